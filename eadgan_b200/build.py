@@ -1,0 +1,29 @@
+"""Build libeadgan.so in-tree: ``python -m eadgan_b200.build`` (nvcc, sm_100a only)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = ["simt_conv.cu", "bn.cu", "elementwise.cu", "spectral_norm.cu", "loss_adam.cu", "tc_conv.cu"]
+
+
+def build(force=False, verbose=False):
+    csrc = os.path.join(HERE, "csrc")
+    out = os.path.join(HERE, "lib", "libeadgan.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(csrc, s) for s in SRC]
+    deps = srcs + [os.path.join(csrc, "common.cuh"), os.path.join(HERE, "..", "include", "eadgan.h")]
+    if not force and os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(d) for d in deps):
+        return out
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-I", os.path.join(HERE, "..", "include"),
+           "-diag-suppress", "177", *srcs, "-o", out]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.run(cmd, check=True)
+    return out
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,342 @@
+// BatchNorm2d (training + eval) as HBM-bound streaming kernels, split into
+// reduce / finalize / apply halves so a cross-rank all-reduce of the [2C] fp64
+// partial sums can be placed between them (SyncBN).
+// Reference call sites: nn.BatchNorm2d at celebA/EAD-GAN_celebA.py:79,83,87,
+// dSprites/rp.py:130,134,138, MNIST/EAD-GAN_rpqmnxy.py:80,83,87,145 (eps = 0.8 there).
+// Semantics follow torch F.batch_norm: biased variance for normalisation, unbiased
+// for running_var, momentum 0.1.
+//
+// Two memory layouts are handled without per-element integer division:
+//   kind 0  dense NCHW   : a "row" is one (n,c) plane of h*w contiguous elements
+//   kind 1  NHWC rows    : a "row" is one (n,y) line of w*c contiguous elements
+//                          (halo-padded private buffers: sc==1, sw==c, any sh/sn)
+// Algorithmic bytes / element: stats 4 (fp32) or 2 (bf16) read; apply read+write;
+// bwd_reduce 2 reads; bwd_apply 2 reads + 1 write.
+#include "common.cuh"
+
+namespace {
+
+struct Geo {
+  int kind, n, c, h, w;
+  int rows, inner;
+};
+
+int classify(const eadgan_tensor4* t, int c, int h, int w) {
+  if (t->sw == 1 && t->sh == w) return 0;
+  if (t->sc == 1 && t->sw == c) return 1;
+  if (h == 1 && w == 1) return 0;  // [N,C,1,1]: any strides, inner run of length 1
+  return -1;
+}
+
+__device__ __forceinline__ int64_t row_base(const eadgan_tensor4& t, const Geo& g, int row) {
+  if (g.kind == 0) {
+    const int b = row / g.c, ch = row - b * g.c;
+    return (int64_t)b * t.sn + (int64_t)ch * t.sc;
+  }
+  const int b = row / g.h, y = row - b * g.h;
+  return (int64_t)b * t.sn + (int64_t)y * t.sh;
+}
+
+constexpr int CHUNK = 2048;  // inner elements per warp job (kind 0)
+
+// ---------------- per-channel reductions -------------------------------------------------
+// F(i_global_offsets...) returns the two values to accumulate for one element.
+// kind 0: warp job = (row, chunk); lanes stride the contiguous run; one channel per job.
+template <class F>
+__device__ void reduce_kind0(const Geo g, double* sums, F f) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int chunks = (g.inner + CHUNK - 1) / CHUNK;
+  const int64_t jobs = (int64_t)g.rows * chunks;
+  for (int64_t job = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); job < jobs;
+       job += (int64_t)gridDim.x * warps_per_block) {
+    const int row = (int)(job / chunks);
+    const int ck = (int)(job - (int64_t)row * chunks);
+    const int ch = row % g.c;
+    const int i_end = min(g.inner, (ck + 1) * CHUNK);
+    double s0 = 0.0, s1 = 0.0;
+    float a0 = 0.f, a1 = 0.f;
+    int cnt = 0;
+    for (int i = ck * CHUNK + lane; i < i_end; i += 32) {
+      float v0, v1;
+      f(row, i, ch, v0, v1);
+      a0 += v0;
+      a1 += v1;
+      if (++cnt == 16) { s0 += a0; s1 += a1; a0 = a1 = 0.f; cnt = 0; }
+    }
+    s0 += a0;
+    s1 += a1;
+    s0 = eg_warp_sum_d(s0);
+    s1 = eg_warp_sum_d(s1);
+    if (lane == 0) {
+      atomicAdd(&sums[ch], s0);
+      atomicAdd(&sums[g.c + ch], s1);
+    }
+  }
+}
+
+// kind 1: thread <-> channel (channels contiguous); blockDim.x = 256 covers `cb` channels
+// times 256/cb pixel lanes; a block walks pixels in grid-stride; smem reduce; atomics.
+template <class F>
+__device__ void reduce_kind1(const Geo g, double* sums, F f) {
+  __shared__ double sh0[256], sh1[256];
+  const int cb = g.c < 256 ? g.c : 256;      // channels per pass (c is a multiple of cb or < 256)
+  const int lanes = 256 / cb;                // pixel lanes per block (>=1)
+  const int tch = threadIdx.x % cb, tl = threadIdx.x / cb;
+  const int64_t pixels = (int64_t)g.rows * g.w;
+  for (int c0 = 0; c0 < g.c; c0 += cb) {
+    const int ch = c0 + tch;
+    double s0 = 0.0, s1 = 0.0;
+    if (tl < lanes && ch < g.c) {
+      float a0 = 0.f, a1 = 0.f;
+      int cnt = 0;
+      for (int64_t p = (int64_t)blockIdx.x * lanes + tl; p < pixels; p += (int64_t)gridDim.x * lanes) {
+        const int row = (int)(p / g.w);
+        const int x = (int)(p - (int64_t)row * g.w);
+        float v0, v1;
+        f(row, x * g.c + ch, ch, v0, v1);
+        a0 += v0;
+        a1 += v1;
+        if (++cnt == 16) { s0 += a0; s1 += a1; a0 = a1 = 0.f; cnt = 0; }
+      }
+      s0 += a0;
+      s1 += a1;
+    }
+    sh0[threadIdx.x] = s0;
+    sh1[threadIdx.x] = s1;
+    __syncthreads();
+    if (threadIdx.x < cb && ch < g.c) {
+      double r0 = 0.0, r1 = 0.0;
+      for (int l = 0; l < lanes; ++l) { r0 += sh0[l * cb + threadIdx.x]; r1 += sh1[l * cb + threadIdx.x]; }
+      atomicAdd(&sums[ch], r0);
+      atomicAdd(&sums[g.c + ch], r1);
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_stats_kernel(eadgan_tensor4 x, Geo g, double* sums) {
+  auto f = [&](int row, int i, int ch, float& v0, float& v1) {
+    const float v = eg_ld(x.ptr, row_base(x, g, row) + i, x.dtype);
+    v0 = v;
+    v1 = v * v;
+  };
+  if (g.kind == 0) reduce_kind0(g, sums, f); else reduce_kind1(g, sums, f);
+}
+
+struct BwdArgs {
+  eadgan_tensor4 dy, x, y, dx;
+  const float *mean, *invstd, *gamma, *beta;
+  const double* sums;
+  double count;
+  int act;
+  float slope;
+};
+
+// dz = dy * act'(y);  xhat = (x - mean) * invstd
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(BwdArgs a, Geo g, double* sums) {
+  auto f = [&](int row, int i, int ch, float& v0, float& v1) {
+    float dz = eg_ld(a.dy.ptr, row_base(a.dy, g, row) + i, a.dy.dtype);
+    if (a.act != EADGAN_ACT_NONE) {
+      const float yv = eg_ld(a.y.ptr, row_base(a.y, g, row) + i, a.y.dtype);
+      dz *= eg_act_grad(yv, a.act, a.slope);
+    }
+    const float xv = eg_ld(a.x.ptr, row_base(a.x, g, row) + i, a.x.dtype);
+    v0 = dz;
+    v1 = dz * (xv - a.mean[ch]) * a.invstd[ch];
+  };
+  if (g.kind == 0) reduce_kind0(g, sums, f); else reduce_kind1(g, sums, f);
+}
+
+// ---------------- elementwise passes -----------------------------------------------------
+template <class F>
+__device__ void foreach_elem(const Geo g, F f) {
+  // block job = (row, 1024-element chunk); threads stride the contiguous run
+  const int chunks = (g.inner + 1023) / 1024;
+  const int64_t jobs = (int64_t)g.rows * chunks;
+  for (int64_t job = blockIdx.x; job < jobs; job += gridDim.x) {
+    const int row = (int)(job / chunks);
+    const int ck = (int)(job - (int64_t)row * chunks);
+    const int i_end = min(g.inner, (ck + 1) * 1024);
+    const int ch_row = row % g.c;
+    for (int i = ck * 1024 + threadIdx.x; i < i_end; i += blockDim.x)
+      f(row, i, g.kind == 0 ? ch_row : i % g.c);
+  }
+}
+
+struct ApplyArgs {
+  eadgan_tensor4 x, y;
+  const float *mean, *invstd, *gamma, *beta;
+  int act;
+  float slope;
+  float eps;
+  int eval;  // mean=running_mean, invstd=running_var (converted on the fly)
+};
+
+__global__ void __launch_bounds__(256) bn_apply_kernel(ApplyArgs a, Geo g) {
+  foreach_elem(g, [&](int row, int i, int ch) {
+    const float xv = eg_ld(a.x.ptr, row_base(a.x, g, row) + i, a.x.dtype);
+    const float is = a.eval ? rsqrtf(a.invstd[ch] + a.eps) : a.invstd[ch];
+    const float ga = a.gamma ? a.gamma[ch] : 1.f, be = a.beta ? a.beta[ch] : 0.f;
+    float v = (xv - a.mean[ch]) * is * ga + be;
+    v = eg_act(v, a.act, a.slope);
+    eg_st(a.y.ptr, row_base(a.y, g, row) + i, a.y.dtype, v);
+  });
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BwdArgs a, Geo g) {
+  const double inv_count = 1.0 / a.count;
+  foreach_elem(g, [&](int row, int i, int ch) {
+    float dz = eg_ld(a.dy.ptr, row_base(a.dy, g, row) + i, a.dy.dtype);
+    if (a.act != EADGAN_ACT_NONE) {
+      const float yv = eg_ld(a.y.ptr, row_base(a.y, g, row) + i, a.y.dtype);
+      dz *= eg_act_grad(yv, a.act, a.slope);
+    }
+    const float xv = eg_ld(a.x.ptr, row_base(a.x, g, row) + i, a.x.dtype);
+    const float is = a.invstd[ch];
+    const float xhat = (xv - a.mean[ch]) * is;
+    const float m_dz = (float)(a.sums[ch] * inv_count);
+    const float m_dzx = (float)(a.sums[g.c + ch] * inv_count);
+    const float ga = a.gamma ? a.gamma[ch] : 1.f;
+    const float v = ga * is * (dz - m_dz - xhat * m_dzx);
+    eg_st(a.dx.ptr, row_base(a.dx, g, row) + i, a.dx.dtype, v);
+  });
+}
+
+__global__ void bn_finalize_kernel(const double* sums, double count, int c, float eps, float momentum,
+                                   float* mean, float* invstd, float* rmean, float* rvar) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double m = sums[ch] / count;
+  double var = sums[c + ch] / count - m * m;
+  if (var < 0.0) var = 0.0;
+  mean[ch] = (float)m;
+  invstd[ch] = (float)(1.0 / sqrt(var + (double)eps));
+  if (rmean) rmean[ch] = (1.f - momentum) * rmean[ch] + momentum * (float)m;
+  if (rvar) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    rvar[ch] = (1.f - momentum) * rvar[ch] + momentum * (float)unbiased;
+  }
+}
+
+int make_geo(Geo* g, int n, int c, int h, int w, const eadgan_tensor4* const* ts, int nt,
+             const char* who) {
+  EG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, EADGAN_ERR_INVALID, "%s: bad extents", who);
+  int kind = -2;
+  for (int i = 0; i < nt; ++i) {
+    if (!ts[i]) continue;
+    EG_REQUIRE(ts[i]->ptr != nullptr, EADGAN_ERR_INVALID, "%s: NULL tensor", who);
+    const int k = classify(ts[i], c, h, w);
+    EG_REQUIRE(k >= 0, EADGAN_ERR_UNSUPPORTED,
+               "%s: tensor is neither dense NCHW nor channel-fastest NHWC rows", who);
+    EG_REQUIRE(kind == -2 || kind == k, EADGAN_ERR_UNSUPPORTED, "%s: mixed layouts", who);
+    kind = k;
+  }
+  g->kind = kind; g->n = n; g->c = c; g->h = h; g->w = w;
+  if (kind == 0) { g->rows = n * c; g->inner = h * w; }
+  else { g->rows = n * h; g->inner = w * c; }
+  if (kind == 1)
+    EG_REQUIRE(c <= 256 || c % 256 == 0, EADGAN_ERR_UNSUPPORTED, "%s: NHWC needs c<=256 or c%%256==0", who);
+  return 0;
+}
+
+int reduce_grid(const Geo& g) {
+  int64_t jobs;
+  if (g.kind == 0) jobs = ((int64_t)g.rows * ((g.inner + CHUNK - 1) / CHUNK) + 7) / 8;
+  else jobs = ((int64_t)g.rows * g.w + 63) / 64;
+  const int cap = 16 * eg_sm_count();
+  return (int)(jobs < 1 ? 1 : (jobs > cap ? cap : jobs));
+}
+int elem_grid(const Geo& g) {
+  const int64_t jobs = (int64_t)g.rows * ((g.inner + 1023) / 1024);
+  const int cap = 32 * eg_sm_count();
+  return (int)(jobs > cap ? cap : jobs);
+}
+
+}  // namespace
+
+extern "C" int eadgan_bn_stats(const eadgan_tensor4* x, int n, int c, int h, int w, double* sums,
+                               void* stream) {
+  Geo g;
+  const eadgan_tensor4* ts[] = {x};
+  EG_REQUIRE(x && sums, EADGAN_ERR_INVALID, "bn_stats: NULL argument");
+  if (int e = make_geo(&g, n, c, h, w, ts, 1, "bn_stats")) return e;
+  bn_stats_kernel<<<reduce_grid(g), 256, 0, (cudaStream_t)stream>>>(*x, g, sums);
+  EG_LAUNCH_CHECK("bn_stats_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_bn_finalize(const double* sums, double count, int c, float eps, float momentum,
+                                  float* mean, float* invstd, float* running_mean,
+                                  float* running_var, void* stream) {
+  EG_REQUIRE(sums && mean && invstd && c > 0 && count > 0, EADGAN_ERR_INVALID, "bn_finalize: bad arguments");
+  bn_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, count, c, eps, momentum, mean,
+                                                                       invstd, running_mean, running_var);
+  EG_LAUNCH_CHECK("bn_finalize_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_bn_apply(const eadgan_tensor4* x, int n, int c, int h, int w, const float* mean,
+                               const float* invstd, const float* gamma, const float* beta, int act,
+                               float slope, const eadgan_tensor4* y, void* stream) {
+  Geo g;
+  const eadgan_tensor4* ts[] = {x, y};
+  EG_REQUIRE(x && y && mean && invstd, EADGAN_ERR_INVALID, "bn_apply: NULL argument");
+  if (int e = make_geo(&g, n, c, h, w, ts, 2, "bn_apply")) return e;
+  ApplyArgs a{*x, *y, mean, invstd, gamma, beta, act, slope, 0.f, 0};
+  bn_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
+  EG_LAUNCH_CHECK("bn_apply_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_bn_eval(const eadgan_tensor4* x, int n, int c, int h, int w,
+                              const float* running_mean, const float* running_var, float eps,
+                              const float* gamma, const float* beta, int act, float slope,
+                              const eadgan_tensor4* y, void* stream) {
+  Geo g;
+  const eadgan_tensor4* ts[] = {x, y};
+  EG_REQUIRE(x && y && running_mean && running_var, EADGAN_ERR_INVALID, "bn_eval: NULL argument");
+  if (int e = make_geo(&g, n, c, h, w, ts, 2, "bn_eval")) return e;
+  ApplyArgs a{*x, *y, running_mean, running_var, gamma, beta, act, slope, eps, 1};
+  bn_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
+  EG_LAUNCH_CHECK("bn_apply_kernel(eval)");
+  return 0;
+}
+
+extern "C" int eadgan_bn_bwd_reduce(const eadgan_tensor4* dy, const eadgan_tensor4* x,
+                                    const eadgan_tensor4* y, int n, int c, int h, int w,
+                                    const float* mean, const float* invstd, const float* gamma,
+                                    const float* beta, int act, float slope, double* sums,
+                                    void* stream) {
+  Geo g;
+  EG_REQUIRE(dy && x && mean && invstd && sums, EADGAN_ERR_INVALID, "bn_bwd_reduce: NULL argument");
+  EG_REQUIRE(act == EADGAN_ACT_NONE || y, EADGAN_ERR_INVALID, "bn_bwd_reduce: fused activation needs y");
+  const eadgan_tensor4* ts[] = {dy, x, act != EADGAN_ACT_NONE ? y : nullptr};
+  if (int e = make_geo(&g, n, c, h, w, ts, 3, "bn_bwd_reduce")) return e;
+  BwdArgs a{};
+  a.dy = *dy; a.x = *x; if (y) a.y = *y;
+  a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+  bn_bwd_reduce_kernel<<<reduce_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g, sums);
+  EG_LAUNCH_CHECK("bn_bwd_reduce_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_bn_bwd_apply(const eadgan_tensor4* dy, const eadgan_tensor4* x,
+                                   const eadgan_tensor4* y, int n, int c, int h, int w,
+                                   const float* mean, const float* invstd, const float* gamma,
+                                   const float* beta, int act, float slope, const double* sums,
+                                   double count, const eadgan_tensor4* dx, void* stream) {
+  Geo g;
+  EG_REQUIRE(dy && x && dx && mean && invstd && sums && count > 0, EADGAN_ERR_INVALID,
+             "bn_bwd_apply: NULL argument");
+  EG_REQUIRE(act == EADGAN_ACT_NONE || y, EADGAN_ERR_INVALID, "bn_bwd_apply: fused activation needs y");
+  const eadgan_tensor4* ts[] = {dy, x, dx, act != EADGAN_ACT_NONE ? y : nullptr};
+  if (int e = make_geo(&g, n, c, h, w, ts, 4, "bn_bwd_apply")) return e;
+  BwdArgs a{};
+  a.dy = *dy; a.x = *x; if (y) a.y = *y; a.dx = *dx;
+  a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+  a.sums = sums; a.count = count;
+  bn_bwd_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
+  EG_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return 0;
+}

@@ -1,0 +1,177 @@
+// Legacy torch.nn.utils.spectral_norm (SpectralNorm.compute_weight in
+// torch/nn/utils/spectral_norm.py) as HBM-bound mat-vec passes over W[rows, cols]:
+//   v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v);  W_sn = W / sigma
+// with normalize(x) = x / max(||x||_2, eps), eps = 1e-12, one power iteration per
+// training-mode forward, u/v updated in place (SURVEY.md sections 2.3, 7.3-6).
+// Reference call sites: spectral_norm(...) at celebA/EAD-GAN_celebA.py:110-119,
+// dSprites/rp.py:95-109,165-183, MNIST/EAD-GAN_rpqmnxy.py:107,124,143,161-163.
+// Algorithmic bytes: 3 reads + 1 write of W per forward (16 B / weight).
+#include "common.cuh"
+
+namespace {
+
+// t[j] += sum_{i in row range} W[i,j] * u[i];  block = 128 threads = 128 columns
+__global__ void __launch_bounds__(128) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u,
+                                                     float* __restrict__ t, int rows, int cols, int rows_per_blk) {
+  const int j = blockIdx.x * 128 + threadIdx.x;
+  const int r0 = blockIdx.y * rows_per_blk;
+  const int r1 = min(rows, r0 + rows_per_blk);
+  if (j >= cols) return;
+  float acc = 0.f;
+  int i = r0;
+  for (; i + 4 <= r1; i += 4) {
+    const float a0 = W[(int64_t)i * cols + j], a1 = W[(int64_t)(i + 1) * cols + j];
+    const float a2 = W[(int64_t)(i + 2) * cols + j], a3 = W[(int64_t)(i + 3) * cols + j];
+    acc = fmaf(a0, u[i], acc); acc = fmaf(a1, u[i + 1], acc);
+    acc = fmaf(a2, u[i + 2], acc); acc = fmaf(a3, u[i + 3], acc);
+  }
+  for (; i < r1; ++i) acc = fmaf(W[(int64_t)i * cols + j], u[i], acc);
+  if (gridDim.y == 1) t[j] = acc; else atomicAdd(&t[j], acc);
+}
+
+// single block: out[i] = in[i] / max(||in||, eps)
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                            int n, float eps) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(in[i], in[i], s);
+  s = eg_block_sum(s, red);
+  const float inv = 1.f / fmaxf(sqrtf(s), eps);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i] * inv;
+}
+
+// s[i] = sum_j W[i,j] v[j];  one block per row
+__global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ v,
+                                                    float* __restrict__ s, int rows, int cols) {
+  __shared__ float red[32];
+  const int i = blockIdx.x;
+  const float* wr = W + (int64_t)i * cols;
+  float acc = 0.f;
+  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
+      const float4 a = reinterpret_cast<const float4*>(wr)[j];
+      const float4 b = reinterpret_cast<const float4*>(v)[j];
+      acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
+      acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
+    }
+  } else {
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) acc = fmaf(wr[j], v[j], acc);
+  }
+  acc = eg_block_sum(acc, red);
+  if (threadIdx.x == 0) s[i] = acc;
+}
+
+// single block: if update_u: u = s / max(||s||, eps);  sigma = sum u[i]*s[i]
+__global__ void __launch_bounds__(1024) sn_sigma_kernel(const float* __restrict__ s, float* __restrict__ u, int rows,
+                                                        float eps, int update_u, float* __restrict__ sigma) {
+  __shared__ float red[32];
+  if (update_u) {
+    float q = 0.f;
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) q = fmaf(s[i], s[i], q);
+    q = eg_block_sum(q, red);
+    const float inv = 1.f / fmaxf(sqrtf(q), eps);
+    for (int i = threadIdx.x; i < rows; i += blockDim.x) u[i] = s[i] * inv;
+    __syncthreads();
+  }
+  float d = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) d = fmaf(u[i], s[i], d);
+  d = eg_block_sum(d, red);
+  if (threadIdx.x == 0) *sigma = d;
+}
+
+__global__ void __launch_bounds__(256) sn_scale_kernel(const float* __restrict__ W, const float* __restrict__ sigma,
+                                                       float* __restrict__ out, int64_t n) {
+  const float sg = *sigma;
+  const int64_t tid = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, nth = (int64_t)gridDim.x * blockDim.x;
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    for (int64_t i = tid; i < (n >> 2); i += nth) {
+      float4 a = reinterpret_cast<const float4*>(W)[i];
+      a.x /= sg; a.y /= sg; a.z /= sg; a.w /= sg;
+      reinterpret_cast<float4*>(out)[i] = a;
+    }
+  } else {
+    for (int64_t i = tid; i < n; i += nth) out[i] = W[i] / sg;
+  }
+}
+
+// acc[0] += <a, b>
+__global__ void __launch_bounds__(256) sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                     int64_t n, float* __restrict__ acc) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s = fmaf(a[i], b[i], s);
+  s = eg_block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(acc, s);
+}
+
+// dW_orig[i,j] = dW[i,j]/sigma - (dot/sigma^2) * u[i] * v[j]
+__global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ dW, const float* __restrict__ u,
+                                                     const float* __restrict__ v, const float* __restrict__ sigma,
+                                                     const float* __restrict__ dot, int rows, int cols,
+                                                     float* __restrict__ out) {
+  const float sg = *sigma;
+  const float coef = *dot / (sg * sg);
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    out[i] = dW[i] / sg - coef * u[r] * v[c];
+  }
+}
+
+int grid_for(int64_t n) {
+  int64_t b = (n + 1023) / 1024;
+  const int64_t cap = 16 * (int64_t)eg_sm_count();
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+}  // namespace
+
+extern "C" int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols, float* u, float* v,
+                                        int do_power_iter, float eps, float* sigma, float* w_sn,
+                                        float* scratch, void* stream) {
+  EG_REQUIRE(w_orig && u && v && sigma && scratch && rows > 0 && cols > 0, EADGAN_ERR_INVALID,
+             "spectral_norm_fwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* t = scratch;          // [cols]
+  float* s = scratch + cols;   // [rows]
+  if (do_power_iter) {
+    int col_tiles = (cols + 127) / 128;
+    int splits = (4 * eg_sm_count() + col_tiles - 1) / col_tiles;
+    int max_splits = (rows + 15) / 16;
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    const int rpb = (rows + splits - 1) / splits;
+    splits = (rows + rpb - 1) / rpb;
+    if (splits > 1) EG_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
+    sn_wtu_kernel<<<dim3(col_tiles, splits), 128, 0, st>>>(w_orig, u, t, rows, cols, rpb);
+    EG_LAUNCH_CHECK("sn_wtu_kernel");
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(t, v, cols, eps);
+    EG_LAUNCH_CHECK("sn_normalize_kernel");
+  }
+  sn_wv_kernel<<<rows, 256, 0, st>>>(w_orig, v, s, rows, cols);
+  EG_LAUNCH_CHECK("sn_wv_kernel");
+  sn_sigma_kernel<<<1, 1024, 0, st>>>(s, u, rows, eps, do_power_iter ? 1 : 0, sigma);
+  EG_LAUNCH_CHECK("sn_sigma_kernel");
+  if (w_sn) {
+    const int64_t n = (int64_t)rows * cols;
+    sn_scale_kernel<<<grid_for(n), 256, 0, st>>>(w_orig, sigma, w_sn, n);
+    EG_LAUNCH_CHECK("sn_scale_kernel");
+  }
+  return 0;
+}
+
+extern "C" int eadgan_spectral_norm_bwd(const float* dw_sn, const float* w_orig, const float* u,
+                                        const float* v, const float* sigma, int rows, int cols,
+                                        float* dw_orig, float* scratch, void* stream) {
+  EG_REQUIRE(dw_sn && w_orig && u && v && sigma && dw_orig && scratch && rows > 0 && cols > 0,
+             EADGAN_ERR_INVALID, "spectral_norm_bwd: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = (int64_t)rows * cols;
+  EG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), st));
+  sn_dot_kernel<<<grid_for(n), 256, 0, st>>>(dw_sn, w_orig, n, scratch);
+  EG_LAUNCH_CHECK("sn_dot_kernel");
+  sn_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dw_sn, u, v, sigma, scratch, rows, cols, dw_orig);
+  EG_LAUNCH_CHECK("sn_bwd_kernel");
+  return 0;
+}

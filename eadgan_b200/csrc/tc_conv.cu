@@ -1,0 +1,879 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution for kernel 4, stride 2, pad 1 (the
+// geometry of every heavy layer of EAD-GAN: celebA/EAD-GAN_celebA.py:78-87,113-119,
+// dSprites/rp.py:66-75,95-104,129-141,165-174).  bf16 operands, fp32 accumulation
+// in tensor memory.  Written for sm_100a only.
+//
+// Data layout.  Every activation lives in a private halo-padded NHWC bf16 buffer
+// X[n][H+2][W+2][C] whose 1-pixel halo is zero.  With the halo in memory there is no
+// boundary special case, and both operand gathers become plain TMA *tiled* boxes:
+//
+//  * FPROP (Conv2d forward, ConvTranspose2d input-grad): y[oy,ox] = sum_{ky,kx,c}
+//    Xp[2oy+ky][2ox+kx][c] w[ky][kx][c].  Writing ky=2a+dy, kx=2b+dx, the padded map
+//    is viewed as a 5-D tensor (dx*C+c, j, dy, i, n) with Xp[2i+dy][2j+dx] (space to
+//    depth by strides only, no copy); tap (a,b,dy) of an output tile is the box
+//    [64 ch] x [Tw] x [1] x [Th] x [Tb] at (q*64, ox0+b, dy, oy0+a, n0).
+//    GEMM: M = n*p*q pixels, N = k, K = 16*c ordered (a,b,dy,dx,c).
+//  * DGRAD (ConvTranspose2d forward, Conv2d input-grad): four output-parity
+//    sub-convolutions with 2x2 taps; tap (ty,tx) of parity
+//    (py,px) is the 4-D box at (q*64, j0+1+dx, i0+1+dy, n0) of the small map.
+//    GEMM per parity: M = n*p*q, N = c, K = 4*k.
+//  * WGRAD: dw[ko][kk] = sum_pixels dy[pix][ko] * patch[pix][kk]; both operands are
+//    "MN-major" (the reduction runs over smem rows), 64 pixels per pipeline stage,
+//    split over the pixel dimension, fp32 partials reduced + permuted to [k,c,4,4].
+//
+// Kernel anatomy (all three): 192 threads = warp 0 TMA producer (one elected lane),
+// warp 1 TMEM allocator + single-thread tcgen05.mma issuer, warps 2..5 epilogue
+// (tcgen05.ld 32x32b, one TMEM lane quadrant each).  smem ring of STAGES x (A|B)
+// tiles with 128-byte swizzle, full/empty mbarriers, tcgen05.commit releases slots.
+#include <cuda.h>
+
+#include <mutex>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1;\n\t"
+      "@P bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+      "%7}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+               "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// UMMA shared-memory descriptor, 128-byte swizzle (cute::UMMA::SmemDescriptor, version 1)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;  // LayoutType::SWIZZLE_128B
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::f16: bf16 x bf16 -> fp32
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------
+// kernel parameters
+// ------------------------------------------------------------------------------------
+enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2 };
+
+struct TcParams {
+  int mode;
+  int n, p, q;        // GEMM pixel grid: n images of p x q positions
+  int Tw, Th, Tb;     // tile of 128 positions = Tb x Th x Tw
+  int tiles_y;        // p / Th
+  int N_total;        // output channels of this direction (k for fprop, c for dgrad)
+  int K_ch;           // operand channels: fprop c (big map), dgrad k (small map); gemm: K
+  int nkb;            // number of 64-wide k blocks
+  int qblocks;        // fprop: 2c/64 ; dgrad: k/64
+  // epilogue
+  int act; float slope;
+  int out_f32_nchw, want_stats, mask_mode;
+  int OH, OW;         // output map extents (fprop: p,q ; dgrad: 2p,2q)
+  const float* bias;
+  void* out;
+  const __nv_bfloat16* mask;
+  double* stats;
+  int gemm_m, gemm_n;  // MODE_GEMM extents
+};
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;
+constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BLOCK_N * 16 /*stats*/;
+};
+
+// ------------------------------------------------------------------------------------
+// fprop / dgrad / gemm kernel
+// ------------------------------------------------------------------------------------
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+               const TcParams P) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  double* stat_smem = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [4][BLOCK_N]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y, parity = blockIdx.z;
+  const int py = parity >> 1, px = parity & 1;
+
+  // tile origin
+  int b0 = 0, y0 = 0;
+  if (P.mode != MODE_GEMM) {
+    b0 = (m_tile / P.tiles_y) * P.Tb;
+    y0 = (m_tile % P.tiles_y) * P.Th;
+  }
+  const int n0 = n_tile * BLOCK_N;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+        uint8_t* sb = sa + A_BYTES;
+        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        if (P.mode == MODE_GEMM) {
+          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+        } else if (P.mode == MODE_FPROP) {
+          const int qi = kb % P.qblocks, t = kb / P.qblocks;
+          const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+          tma_load_5d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+        } else {
+          const int qi = kb % P.qblocks, t = kb / P.qblocks;  // t = ty*2+tx
+          const int ty = t >> 1, tx = t & 1;
+          const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+          const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+          tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, parity * P.N_total + n0);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < P.nkb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+        const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          const uint64_t da = make_desc(sa + k * 32, 16, 1024);
+          const uint64_t db = make_desc(sb + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == P.nkb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // ===== epilogue: TMEM -> registers -> global =====
+    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
+    const int row = quad * 32 + lane;   // row of the 128-row tile
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+
+    bool valid;
+    int64_t out_off = 0;     // element offset of (pixel, channel n0) in the output
+    int64_t ch_stride = 1;   // element stride between channels in the output
+    int64_t mask_off = 0;
+    if (P.mode == MODE_GEMM) {
+      const int m = m_tile * BLOCK_M + row;
+      valid = m < P.gemm_m;
+      out_off = (int64_t)m * P.gemm_n + n0;
+    } else {
+      const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
+      const int b = b0 + bl;
+      valid = b < P.n;
+      int oy, ox;
+      if (P.mode == MODE_FPROP) { oy = y0 + yl; ox = xl; }
+      else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
+      const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
+      mask_off = pad_off;
+      if (P.out_f32_nchw) {
+        out_off = (((int64_t)b * P.N_total + n0) * P.OH + oy) * P.OW + ox;
+        ch_stride = (int64_t)P.OH * P.OW;
+      } else {
+        out_off = pad_off;
+      }
+    }
+    const bool f32_out = (P.mode == MODE_GEMM) || P.out_f32_nchw;
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      const bool ch_ok = (P.mode != MODE_GEMM) || (n0 + c0 < P.gemm_n);
+      if (P.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] += __ldg(&P.bias[n0 + c0 + j]);
+      }
+      if (P.want_stats) {
+        // per-channel sum / sum of squares over the 32 pixels of this warp (butterfly),
+        // lane j ends up holding channel c0+j
+        float s1[32], s2[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
+#pragma unroll
+        for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+          for (int j = 0; j < w; ++j) {
+            const bool up = (lane & w) != 0;
+            const float a1 = up ? s1[j] : s1[j + w], k1 = up ? s1[j + w] : s1[j];
+            const float a2 = up ? s2[j] : s2[j + w], k2 = up ? s2[j + w] : s2[j];
+            s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+            s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+          }
+        }
+        // after the butterfly lane l holds the total of channel c0 + l
+        const int chl = lane;
+        stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 0] = (double)s1[0];
+        stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 1] = (double)s2[0];
+      }
+      if (valid && ch_ok) {
+        if (P.act != EADGAN_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = eg_act(v[j], P.act, P.slope);
+        }
+        if (P.mask_mode) {
+          const uint4* mp = reinterpret_cast<const uint4*>(P.mask + mask_off + c0);
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 mv = __ldg(mp + g);
+            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float m_lo = __uint_as_float(mw[e] << 16), m_hi = __uint_as_float(mw[e] & 0xffff0000u);
+              v[g * 8 + e * 2 + 0] *= eg_act_grad(m_lo, P.mask_mode, P.slope);
+              v[g * 8 + e * 2 + 1] *= eg_act_grad(m_hi, P.mask_mode, P.slope);
+            }
+          }
+        }
+        if (f32_out) {
+          float* op = reinterpret_cast<float*>(P.out) + out_off + (int64_t)c0 * ch_stride;
+          if (ch_stride == 1) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+              *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) op[(int64_t)j * ch_stride] = v[j];
+          }
+        } else {
+          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + out_off + c0;
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+    }
+    if (P.want_stats) {
+      // combine the four warps' partials: 128 epilogue threads, one named barrier
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int et = threadIdx.x - 64;  // 0..127
+      for (int ch = et; ch < BLOCK_N; ch += 128) {
+        double a = 0.0, b2 = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { a += stat_smem[(w * BLOCK_N + ch) * 2]; b2 += stat_smem[(w * BLOCK_N + ch) * 2 + 1]; }
+        atomicAdd(&P.stats[n0 + ch], a);
+        atomicAdd(&P.stats[P.N_total + n0 + ch], b2);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------
+// wgrad kernel: acc[ko][kk] = sum_pixels dy[pix][ko] * patch[pix][kk]
+// ------------------------------------------------------------------------------------
+struct WgParams {
+  int n, p, q;
+  int Tw, Th, Tb;       // 64 pixels per stage
+  int tiles_y;          // p / Th
+  int k, c;             // small-map / big-map channels
+  int qblocks;          // 2c/64
+  int steps_total;      // number of 64-pixel steps
+  int steps_per_split;
+  int Ktot;             // 16*c
+  float* partial;       // [splits][k][16c]
+};
+
+template <int BLOCK_N>  // BLOCK_N columns of kk per tile (multiple of 64)
+struct WgCfg {
+  static constexpr int A_B = 2 * 64 * 128;               // two 64-channel boxes x 64 pixels
+  static constexpr int B_B = (BLOCK_N / 64) * 64 * 128;
+  static constexpr int STAGE_BYTES = A_B + B_B;
+  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : 6;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(192, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
+                const WgParams P) {
+  using C = WgCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kk_tile = blockIdx.x, ko_tile = blockIdx.y, split = blockIdx.z;
+  const int step0 = split * P.steps_per_split;
+  const int step1 = min(P.steps_total, step0 + P.steps_per_split);
+  const int nsteps = step1 - step0;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, BLOCK_N);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int st = step0; st < step1; ++st) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * C::STAGE_BYTES;
+        uint8_t* sb = sa + C::A_B;
+        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+        const int b0 = (st / P.tiles_y) * P.Tb;
+        const int y0 = (st % P.tiles_y) * P.Th;
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 64; ++i) {
+          const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
+          const int qi = nb % P.qblocks, t = nb / P.qblocks;
+          const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+          tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
+        }
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);  // both operands MN-major
+    int stage = 0; uint32_t phase = 0;
+    for (int it = 0; it < nsteps; ++it) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+        const uint32_t sb = sa + C::A_B;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 16 pixel rows per MMA
+          const uint64_t da = make_desc(sa + k * 2048, 8192, 1024);
+          const uint64_t db = make_desc(sb + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (it == nsteps - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int ko = ko_tile * 128 + quad * 32 + lane;
+    if (nsteps > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    float* dst = P.partial + ((int64_t)split * P.k + ko) * P.Ktot + (int64_t)kk_tile * BLOCK_N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      float v[32];
+      if (nsteps > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (ko < P.k) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g)
+          *reinterpret_cast<float4*>(dst + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+}
+
+// sum split partials and permute GEMM column order (a,b,dy,dx,c) -> dw[ko][c][ky][kx]
+// block = (ko, 64-channel group); coalesced reads of 16 x 64-float runs, one 4 KB write
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int k, int c,
+                                                           float* __restrict__ dw) {
+  __shared__ float tile[16][65];
+  const int ko = blockIdx.y, c0 = blockIdx.x * 64;
+  const int Ktot = 16 * c;
+  for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+    const int tap = e / 64, cl = e % 64;  // tap = ((a*2+b)*2+dy)*2+dx
+    if (c0 + cl < c) {
+      const int t3 = tap >> 1, dx = tap & 1;
+      const int64_t col = (int64_t)t3 * 2 * c + (int64_t)dx * c + c0 + cl;
+      float s = 0.f;
+      for (int sp = 0; sp < splits; ++sp) s += partial[((int64_t)sp * k + ko) * Ktot + col];
+      const int dy = t3 & 1, bt = (t3 >> 1) & 1, at = t3 >> 2;
+      const int ky = 2 * at + dy, kx = 2 * bt + dx;
+      tile[ky * 4 + kx][cl] = s;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const int cl = e / 16, tp = e % 16;
+    if (c0 + cl < c) dw[((int64_t)ko * c + c0 + cl) * 16 + tp] = tile[tp][cl];
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------
+// Wf[ko][((a*2+b)*2+dy)*2c + dx*c + ci] = w[ko][ci][2a+dy][2b+dx] / sigma
+__global__ void pack_w_fprop_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c,
+                                    __nv_bfloat16* __restrict__ out) {
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  const int64_t total = (int64_t)k * 16 * c;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ko = (int)(i / (16 * c));
+    const int col = (int)(i - (int64_t)ko * 16 * c);
+    const int t3 = col / (2 * c), rem = col - t3 * 2 * c;
+    const int dx = rem / c, ci = rem - dx * c;
+    const int dy = t3 & 1, bt = (t3 >> 1) & 1, at = t3 >> 2;
+    const int ky = 2 * at + dy, kx = 2 * bt + dx;
+    out[i] = __float2bfloat16_rn(w[(((int64_t)ko * c + ci) * 4 + ky) * 4 + kx] * inv);
+  }
+}
+// Wd[(py*2+px)*c + co][(ty*2+tx)*k + ki] = w[ki][co][ky(py,ty)][kx(px,tx)] / sigma
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c,
+                                    __nv_bfloat16* __restrict__ out) {
+  const float inv = sigma ? 1.f / *sigma : 1.f;
+  const int64_t total = (int64_t)4 * c * 4 * k;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int rowi = (int)(i / (4 * k));
+    const int col = (int)(i - (int64_t)rowi * 4 * k);
+    const int par = rowi / c, co = rowi - par * c;
+    const int t = col / k, ki = col - t * k;
+    const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
+    const int ky = py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2);
+    const int kx = px == 0 ? (tx == 0 ? 1 : 3) : (tx == 0 ? 0 : 2);
+    out[i] = __float2bfloat16_rn(w[(((int64_t)ki * c + co) * 4 + ky) * 4 + kx] * inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int encode_map(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+               const uint32_t* box) {
+  EncodeTiledFn enc = get_encode();
+  EG_REQUIRE(enc != nullptr, EADGAN_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  EG_REQUIRE(r == CUDA_SUCCESS, EADGAN_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)", (int)r,
+             rank);
+  return 0;
+}
+
+// 5-D space-to-depth view of the big padded map [n][h+2][w+2][c]
+int map_big_s2d(CUtensorMap* m, const void* base, int n, int c, int h, int w, int Tw, int Th, int Tb) {
+  const uint64_t dims[5] = {(uint64_t)2 * c, (uint64_t)(w + 2) / 2, 2, (uint64_t)(h + 2) / 2, (uint64_t)n};
+  const uint64_t st[4] = {(uint64_t)2 * c * 2, (uint64_t)(w + 2) * c * 2, (uint64_t)2 * (w + 2) * c * 2,
+                          (uint64_t)(h + 2) * (w + 2) * c * 2};
+  const uint32_t box[5] = {64, (uint32_t)Tw, 1, (uint32_t)Th, (uint32_t)Tb};
+  return encode_map(m, base, 5, dims, st, box);
+}
+// 4-D view of the small padded map [n][p+2][q+2][k]
+int map_small(CUtensorMap* m, const void* base, int n, int k, int p, int q, int Tw, int Th, int Tb) {
+  const uint64_t dims[4] = {(uint64_t)k, (uint64_t)(q + 2), (uint64_t)(p + 2), (uint64_t)n};
+  const uint64_t st[3] = {(uint64_t)k * 2, (uint64_t)(q + 2) * k * 2, (uint64_t)(p + 2) * (q + 2) * k * 2};
+  const uint32_t box[4] = {64, (uint32_t)Tw, (uint32_t)Th, (uint32_t)Tb};
+  return encode_map(m, base, 4, dims, st, box);
+}
+int map_matrix(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t st[1] = {cols * 2};
+  const uint32_t box[2] = {64, box_rows};
+  return encode_map(m, base, 2, dims, st, box);
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// tile of `pixels` positions of a p x q grid: Tw = q, Th rows, Tb images
+int pick_tile(int p, int q, int pixels, int* Tw, int* Th, int* Tb) {
+  if (!pow2(q) || !pow2(p) || q > pixels) return -1;
+  *Tw = q;
+  int th = pixels / q;
+  if (th > p) th = p;
+  *Th = th;
+  *Tb = pixels / (q * th);
+  return 0;
+}
+
+template <int BN>
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    attr_set = true;
+  }
+  tc_conv_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(ma, mb, P);
+  EG_LAUNCH_CHECK("tc_conv_kernel");
+  return 0;
+}
+
+int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid,
+                  cudaStream_t st) {
+  switch (bn) {
+    case 32: return launch_conv<32>(ma, mb, P, grid, st);
+    case 64: return launch_conv<64>(ma, mb, P, grid, st);
+    case 128: return launch_conv<128>(ma, mb, P, grid, st);
+    case 256: return launch_conv<256>(ma, mb, P, grid, st);
+  }
+  return eadgan_set_error(EADGAN_ERR_UNSUPPORTED, "tc conv: unsupported BLOCK_N %d", bn);
+}
+
+int pick_bn(int nch) {
+  if (nch % 128 == 0) return 128;
+  if (nch % 64 == 0) return 64;
+  if (nch % 32 == 0) return 32;
+  return -1;
+}
+
+int check_tc(const eadgan_tc_desc* d, const char* who) {
+  EG_REQUIRE(d != nullptr, EADGAN_ERR_INVALID, "%s: NULL desc", who);
+  EG_REQUIRE(d->n > 0 && d->c > 0 && d->k > 0 && d->h >= 2 && d->w >= 2 && (d->h % 2) == 0 && (d->w % 2) == 0,
+             EADGAN_ERR_INVALID, "%s: bad extents", who);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c, void* w_packed,
+                                      void* stream) {
+  EG_REQUIRE(w && w_packed && k > 0 && c > 0, EADGAN_ERR_INVALID, "tc_pack_w_fprop: bad arguments");
+  const int64_t total = (int64_t)k * 16 * c;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
+  pack_w_fprop_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c, (__nv_bfloat16*)w_packed);
+  EG_LAUNCH_CHECK("pack_w_fprop_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c, void* w_packed,
+                                      void* stream) {
+  EG_REQUIRE(w && w_packed && k > 0 && c > 0, EADGAN_ERR_INVALID, "tc_pack_w_dgrad: bad arguments");
+  const int64_t total = (int64_t)k * 16 * c;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
+  pack_w_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c, (__nv_bfloat16*)w_packed);
+  EG_LAUNCH_CHECK("pack_w_dgrad_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const void* w_packed, const float* bias,
+                               void* y, const void* mask, double* stats, void* stream) {
+  if (int e = check_tc(d, "tc_fprop")) return e;
+  EG_REQUIRE(x_pad && w_packed && y, EADGAN_ERR_INVALID, "tc_fprop: NULL pointer");
+  const int p = d->h / 2, q = d->w / 2;
+  EG_REQUIRE((2 * d->c) % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: c=%d must be a multiple of 32", d->c);
+  const int bn = pick_bn(d->k);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: k=%d must be a multiple of 32", d->k);
+  TcParams P{};
+  P.mode = MODE_FPROP; P.n = d->n; P.p = p; P.q = q;
+  EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_fprop: output map %dx%d must be a power of two <= 128 wide", p, q);
+  P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = d->c; P.qblocks = 2 * d->c / 64; P.nkb = 8 * P.qblocks;
+  P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
+  P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+  EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_fprop: mask_mode without mask");
+  EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_fprop: want_stats without stats");
+  CUtensorMap ma, mb;
+  if (int e = map_big_s2d(&ma, x_pad, d->n, d->c, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
+  if (int e = map_matrix(&mb, w_packed, d->k, (uint64_t)16 * d->c, bn)) return e;
+  dim3 grid(((d->n + P.Tb - 1) / P.Tb) * P.tiles_y, d->k / bn, 1);
+  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+}
+
+extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed, const float* bias,
+                               void* dx, const void* mask, double* stats, void* stream) {
+  if (int e = check_tc(d, "tc_dgrad")) return e;
+  EG_REQUIRE(dy_pad && w_packed && dx, EADGAN_ERR_INVALID, "tc_dgrad: NULL pointer");
+  const int p = d->h / 2, q = d->w / 2;
+  EG_REQUIRE(d->k % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: k=%d must be a multiple of 64", d->k);
+  const int bn = pick_bn(d->c);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
+  TcParams P{};
+  P.mode = MODE_DGRAD; P.n = d->n; P.p = p; P.q = q;
+  EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_dgrad: small map %dx%d must be a power of two <= 128 wide", p, q);
+  P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = d->k / 64; P.nkb = 4 * P.qblocks;
+  P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
+  P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+  EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_dgrad: mask_mode without mask");
+  EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_dgrad: want_stats without stats");
+  CUtensorMap ma, mb;
+  if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, P.Tw, P.Th, P.Tb)) return e;
+  if (int e = map_matrix(&mb, w_packed, (uint64_t)4 * d->c, (uint64_t)4 * d->k, bn)) return e;
+  dim3 grid(((d->n + P.Tb - 1) / P.Tb) * P.tiles_y, d->c / bn, 4);
+  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+}
+
+namespace {
+int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
+  const int p = d->h / 2, q = d->w / 2;
+  EG_REQUIRE(d->k % 128 == 0 || d->k == 64, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: k=%d must be 64 or a multiple of 128", d->k);
+  EG_REQUIRE((2 * d->c) % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: c=%d must be a multiple of 32", d->c);
+  P->n = d->n; P->p = p; P->q = q; P->k = d->k; P->c = d->c;
+  EG_REQUIRE(pick_tile(p, q, 64, &P->Tw, &P->Th, &P->Tb) == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_wgrad: small map %dx%d must be a power of two <= 64 wide", p, q);
+  P->tiles_y = p / P->Th;
+  P->qblocks = 2 * d->c / 64;
+  P->Ktot = 16 * d->c;
+  P->steps_total = ((d->n + P->Tb - 1) / P->Tb) * P->tiles_y;
+  *bn = (P->Ktot % 256 == 0) ? 256 : (P->Ktot % 128 == 0 ? 128 : 64);
+  const int tiles = (P->Ktot / *bn) * ((d->k + 127) / 128);
+  int s = (2 * eg_sm_count() + tiles - 1) / tiles;
+  const int max_s = (P->steps_total + 7) / 8;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  P->steps_per_split = (P->steps_total + s - 1) / s;
+  *splits = (P->steps_total + P->steps_per_split - 1) / P->steps_per_split;
+  return 0;
+}
+
+template <int BN>
+int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& P, dim3 grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM));
+    attr_set = true;
+  }
+  tc_wgrad_kernel<BN><<<grid, 192, WgCfg<BN>::SMEM, st>>>(mdy, mx, P);
+  EG_LAUNCH_CHECK("tc_wgrad_kernel");
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t eadgan_tc_workspace_bytes(const eadgan_tc_desc* d, int direction) {
+  if (direction != 2 || !d) return 0;
+  WgParams P{};
+  int bn = 0, splits = 0;
+  if (wgrad_plan(d, &P, &bn, &splits) != 0) return 0;
+  const int k_pad = ((d->k + 127) / 128) * 128;
+  return (size_t)splits * k_pad * (size_t)P.Ktot * sizeof(float);
+}
+
+extern "C" int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const void* dy_pad, float* dw,
+                               void* workspace, size_t ws_bytes, void* stream) {
+  if (int e = check_tc(d, "tc_wgrad")) return e;
+  EG_REQUIRE(x_pad && dy_pad && dw && workspace, EADGAN_ERR_INVALID, "tc_wgrad: NULL pointer");
+  WgParams P{};
+  int bn = 0, splits = 0;
+  if (int e = wgrad_plan(d, &P, &bn, &splits)) return e;
+  const int k_pad = ((d->k + 127) / 128) * 128;
+  const size_t need = (size_t)splits * k_pad * (size_t)P.Ktot * sizeof(float);
+  EG_REQUIRE(ws_bytes >= need, EADGAN_ERR_WORKSPACE, "tc_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  P.partial = (float*)workspace;
+  // partial rows are indexed with stride P.k: use the padded k so out-of-range rows stay in bounds
+  WgParams PK = P;
+  PK.k = k_pad;
+  CUtensorMap mdy, mx;
+  if (int e = map_small(&mdy, dy_pad, d->n, d->k, P.p, P.q, P.Tw, P.Th, P.Tb)) return e;
+  if (int e = map_big_s2d(&mx, x_pad, d->n, d->c, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
+  dim3 grid(P.Ktot / bn, k_pad / 128, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  switch (bn) {
+    case 64: rc = launch_wgrad<64>(mdy, mx, PK, grid, st); break;
+    case 128: rc = launch_wgrad<128>(mdy, mx, PK, grid, st); break;
+    default: rc = launch_wgrad<256>(mdy, mx, PK, grid, st); break;
+  }
+  if (rc) return rc;
+  wgrad_reduce_kernel<<<dim3((d->c + 63) / 64, d->k), 256, 0, st>>>(P.partial, splits, k_pad, d->c, dw);
+  EG_LAUNCH_CHECK("wgrad_reduce_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f32, int m, int n, int kk,
+                              void* stream) {
+  EG_REQUIRE(a_bf16 && b_bf16 && c_f32 && m > 0 && n > 0 && kk > 0, EADGAN_ERR_INVALID, "tc_gemm: bad arguments");
+  EG_REQUIRE(kk % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: K=%d must be a multiple of 64", kk);
+  const int bn = pick_bn(n);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: N=%d must be a multiple of 32", n);
+  TcParams P{};
+  P.mode = MODE_GEMM; P.nkb = kk / 64; P.gemm_m = m; P.gemm_n = n; P.out = c_f32; P.N_total = n;
+  CUtensorMap ma, mb;
+  if (int e = map_matrix(&ma, a_bf16, m, kk, 128)) return e;
+  if (int e = map_matrix(&mb, b_bf16, n, kk, bn)) return e;
+  dim3 grid((m + 127) / 128, n / bn, 1);
+  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+}

@@ -1,0 +1,26 @@
+"""``python -m eadgan_b200.run <reference_script.py> [script args]``
+
+Patches torch (eadgan_b200.patch) and runs the unmodified reference training script
+with ``runpy`` from the current working directory, which must hold whatever dataset /
+artefact files the script opens.
+"""
+import os
+import runpy
+import sys
+
+
+def main():
+    if len(sys.argv) < 2:
+        print(__doc__)
+        raise SystemExit(2)
+    script = os.path.abspath(sys.argv[1])
+    from . import parallel, patch
+    parallel.init_from_env()
+    patch.patch()
+    sys.argv = [script] + sys.argv[2:]
+    sys.path.insert(0, os.path.dirname(script))
+    runpy.run_path(script, run_name="__main__")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,108 @@
+"""Host-side helpers for the tcgen05 path: private halo-padded NHWC bf16 buffers, weight
+repacking and thin wrappers over the eadgan_tc_* entry points (include/eadgan.h)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_NONE, call, ptr, stream, t4
+
+
+def alloc_padded(n, h, w, c, device):
+    """[n, h+2, w+2, c] bf16 with a zero halo (interior is written by a kernel epilogue)."""
+    return torch.zeros((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
+
+
+def interior(xp):
+    """logical [n, c, h, w] view of the interior of a padded NHWC buffer."""
+    n, hp, wp, c = xp.shape
+    return xp.permute(0, 3, 1, 2)[:, :, 1:hp - 1, 1:wp - 1]
+
+
+def to_padded(x):
+    """fp32/bf16 NCHW tensor -> padded NHWC bf16 (copy4 kernel)."""
+    n, c, h, w = x.shape
+    xp = alloc_padded(n, h, w, c, x.device)
+    src, dst = t4(x), t4(interior(xp))
+    call("eadgan_copy4", C.byref(src), C.byref(dst), n, c, h, w, stream())
+    return xp
+
+
+def from_padded(xp, dtype=torch.float32):
+    n, hp, wp, c = xp.shape
+    out = torch.empty((n, c, hp - 2, wp - 2), device=xp.device, dtype=dtype)
+    src, dst = t4(interior(xp)), t4(out)
+    call("eadgan_copy4", C.byref(src), C.byref(dst), n, c, hp - 2, wp - 2, stream())
+    return out
+
+
+def pack_w(w, sigma=None, direction="fprop"):
+    """fp32 [k, c, 4, 4] -> bf16 GEMM operand ([k,16c] for fprop, [4c,4k] for dgrad), / sigma."""
+    k, c = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (4, 4)
+    out = torch.empty(k * 16 * c, device=w.device, dtype=torch.bfloat16)
+    call("eadgan_tc_pack_w_fprop" if direction == "fprop" else "eadgan_tc_pack_w_dgrad",
+         ptr(w.contiguous()), ptr(sigma), k, c, ptr(out), stream())
+    return out
+
+
+def _desc(n, c, h, w, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, want_stats=False, mask_mode=0):
+    return L.TcDesc(n, c, h, w, k, act, float(slope), int(out_f32_nchw), int(want_stats), int(mask_mode))
+
+
+def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
+          out=None):
+    """big map xp [n,h+2,w+2,c] -> small map [n,p+2,q+2,k] (or fp32 NCHW [n,k,p,q])."""
+    n, hp, wp, c = xp.shape
+    h, w = hp - 2, wp - 2
+    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode)
+    if out is None:
+        out = (torch.empty((n, k, h // 2, w // 2), device=xp.device, dtype=torch.float32) if out_f32_nchw
+               else alloc_padded(n, h // 2, w // 2, k, xp.device))
+    call("eadgan_tc_fprop", C.byref(d), ptr(xp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), stream())
+    return out
+
+
+def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
+          out=None):
+    """small map yp [n,p+2,q+2,k] -> big map [n,2p+2,2q+2,c] (or fp32 NCHW [n,c,2p,2q])."""
+    n, pp, qp, k = yp.shape
+    h, w = 2 * (pp - 2), 2 * (qp - 2)
+    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode)
+    if out is None:
+        out = (torch.empty((n, c, h, w), device=yp.device, dtype=torch.float32) if out_f32_nchw
+               else alloc_padded(n, h, w, c, yp.device))
+    call("eadgan_tc_dgrad", C.byref(d), ptr(yp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), stream())
+    return out
+
+
+_ws_cache = {}
+
+
+def wgrad(xp, yp):
+    """dw[k,c,4,4] fp32 from the big map xp and the small map yp (both padded NHWC bf16)."""
+    n, hp, wp, c = xp.shape
+    k = yp.shape[3]
+    d = _desc(n, c, hp - 2, wp - 2, k)
+    need = L.lib().eadgan_tc_workspace_bytes(C.byref(d), 2)
+    if need == 0:
+        raise RuntimeError(f"tc wgrad: unsupported geometry n={n} c={c} h={hp - 2} k={k}")
+    key = (xp.device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=xp.device, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    dw = torch.empty((k, c, 4, 4), device=xp.device, dtype=torch.float32)
+    call("eadgan_tc_wgrad", C.byref(d), ptr(xp), ptr(yp), ptr(dw), ptr(ws), C.c_size_t(ws.numel()), stream())
+    return dw
+
+
+def gemm(a, b):
+    """C[m,n] fp32 = A[m,k] bf16 @ B[n,k]^T bf16 through the tcgen05 mainloop."""
+    m, kk = a.shape
+    n = b.shape[0]
+    c = torch.empty((m, n), device=a.device, dtype=torch.float32)
+    call("eadgan_tc_gemm", ptr(a.contiguous()), ptr(b.contiguous()), ptr(c), m, n, kk, stream())
+    return c

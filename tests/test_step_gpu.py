@@ -1,0 +1,63 @@
+"""-m gpu: one full CelebA training step (three phases, three Adams) through the drop-in
+modules vs the oracle restatement (stock torch fp32, TF32 off) on identical seeded inputs
+and identical seeded random-init weights.  Protocol of SURVEY.md section 7.3-1: tensor-
+normalised max error per gradient tensor; Adam sign noise means post-step weights are
+compared through the update magnitude, not bit-wise."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_pair(cuda, B, precision):
+    import os
+    os.environ["EADGAN_PRECISION"] = precision
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle import torch_oracle as O
+    imgs = O.synth_celeba_images(B, 0)
+    draws = O.sample_celeba(np.random.RandomState(0), B)
+    st = O.build_celeba(seed=0, device=cuda)
+    ref = O.step_celeba(st, imgs.to(cuda), draws)
+    ours = CelebAStep(seed=0, device=cuda)
+    rec = []
+    losses = ours(imgs.to(cuda), draws["z"].to(cuda), draws["code"].to(cuda), draws["labels"].to(cuda), record=rec)
+    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
+
+
+def test_celeba_step_fp32(cuda):
+    ref, rec, losses, st, ours = _run_pair(cuda, 8, "fp32")
+    for k in ("g_loss", "d_loss", "info_loss"):
+        assert abs(losses[k] - ref["losses"][k]) <= 2e-5 * max(1.0, abs(ref["losses"][k])), (k, losses, ref["losses"])
+    # phase G starts from identical weights: gradients carry the tight bound
+    for go, gr in zip(rec[0]["grads"], ref["phases"][0]["grads"]):
+        assert rel_err(go, gr) <= 1e-4
+    # later phases start from Adam-updated weights (lr * sign(g) noise): looser bound
+    for ph in (1, 2):
+        errs = [rel_err(go, gr) for go, gr in zip(rec[ph]["grads"], ref["phases"][ph]["grads"])]
+        assert max(errs) <= 5e-2, (ph, errs)
+    # BN running statistics and spectral-norm vectors after the whole step
+    so, sr = ours.G.state_dict(), st["G"].state_dict()
+    for k in sr:
+        if "running" in k:
+            assert rel_err(so[k], sr[k]) <= 1e-4, k
+        if "num_batches" in k:
+            assert int(so[k]) == int(sr[k]) == 2
+    so, sr = ours.D.state_dict(), st["D"].state_dict()
+    for k in sr:
+        if k.endswith("_u") or k.endswith("_v"):
+            assert rel_err(so[k], sr[k]) <= 1e-3, k
+
+
+def test_celeba_state_dict_roundtrip(cuda):
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle import torch_oracle as O
+    ours = CelebAStep(seed=1, device=cuda)
+    st = O.build_celeba(seed=2, device=cuda)
+    st["G"].load_state_dict(ours.G.state_dict())
+    st["D"].load_state_dict(ours.D.state_dict())
+    ours.G.load_state_dict(st["G"].state_dict())
+    ours.D.load_state_dict(st["D"].state_dict())
+    assert list(ours.D.state_dict().keys()) == list(st["D"].state_dict().keys())
