@@ -49,8 +49,8 @@ _I, _F, _D, _L = C.c_int, C.c_float, C.c_double, C.c_int64
 
 # name -> argtypes (every function returns int status unless listed in _SPECIAL)
 _PROTOS = {
-    "eadgan_conv_fprop": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _P],
-    "eadgan_conv_dgrad": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _P],
+    "eadgan_conv_fprop": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _T4, _I, _F, _P],
+    "eadgan_conv_dgrad": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _T4, _I, _F, _P],
     "eadgan_conv_wgrad": [C.POINTER(ConvDesc), _T4, _T4, _P, _P],
     "eadgan_channel_sum": [_T4, _I, _I, _I, _I, _P, _P],
     "eadgan_tc_pack_w_fprop": [_P, _P, _I, _I, _P, _P],
@@ -82,13 +82,14 @@ _PROTOS = {
     "eadgan_ce_bwd": [_P, _P, _P, _I, _I, _P, _P],
     "eadgan_mi_fwd": [_P, _P, _I, _I, _P, _P],
     "eadgan_mi_bwd": [_P, _P, _P, _I, _I, _P, _P],
-    "eadgan_adam_step": [C.POINTER(AdamTensors), _F, _F, _F, _D, _D, _F, _P],
+    "eadgan_adam_step": [C.POINTER(AdamTensors), _D, _D, _D, _D, _D, _F, _P],
     "eadgan_fill_f32": [_P, _L, _F, _P],
 }
 _SPECIAL = {
     "eadgan_last_error": ([], C.c_char_p),
     "eadgan_version": ([], C.c_int),
     "eadgan_sm_count": ([], C.c_int),
+    "eadgan_kernel_launches": ([], C.c_int64),
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
 }
 EXPORTED = sorted(list(_PROTOS) + list(_SPECIAL))
@@ -117,10 +118,53 @@ def lib():
     return _lib
 
 
+_prof = None  # list of (name, flops, start_event, end_event) while profiling
+
+
+def _flops(name, args):
+    """algorithmic FLOPs (2*MAC) of one convolution-family call, from its descriptor."""
+    try:
+        d = args[0]._obj
+    except AttributeError:
+        return 0
+    if isinstance(d, ConvDesc):
+        return 2 * d.n * d.p * d.q * d.k * d.c * d.r * d.s
+    if isinstance(d, TcDesc):
+        return 2 * d.n * (d.h // 2) * (d.w // 2) * d.k * d.c * 16
+    return 0
+
+
+def profile_start():
+    """time every C-ABI call with CUDA events on the launching stream (bench.py roofline leg)."""
+    global _prof
+    _prof = []
+
+
+def profile_stop():
+    """-> {entry point: {"calls", "ms", "flops"}}"""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, fl, e0, e1 in rec or []:
+        r = out.setdefault(name, {"calls": 0, "ms": 0.0, "flops": 0})
+        r["calls"] += 1
+        r["ms"] += e0.elapsed_time(e1)
+        r["flops"] += fl
+    return out
+
+
 def call(name, *args):
     """Invoke a status-returning entry point; raise RuntimeError on failure."""
     global launches
-    rc = getattr(lib(), name)(*args)
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(lib(), name)(*args)
+        e1.record()
+        _prof.append((name, _flops(name, args), e0, e1))
+    else:
+        rc = getattr(lib(), name)(*args)
     launches += 1
     if rc != 0:
         msg = lib().eadgan_last_error()

@@ -1,3 +1,322 @@
-"""placeholder; replaced below"""
+"""bf16 tensor-core execution of a whole ``nn.Sequential`` conv stack as ONE autograd node.
+
+When ``EADGAN_PRECISION=bf16`` (default), a Sequential made only of
+  Conv2d | ConvTranspose2d  [+ BatchNorm2d]  [+ LeakyReLU | ReLU | Tanh | Sigmoid]
+groups (every G / D / Encoder trunk of the reference: celebA/EAD-GAN_celebA.py:75-92,
+109-122; dSprites/rp.py:65-76,94-105,128-142,164-175) is run by ``_ChainFn``:
+
+  * module-boundary tensors stay ordinary fp32 NCHW; everything in between lives in PRIVATE
+    halo-padded NHWC bf16 buffers [n, h+2, w+2, c];
+  * k4 s2 p1 layers with tensor-core-friendly channel counts run on the tcgen05/TMEM/TMA
+    kernels (csrc/tc_conv.cu): Conv forward = fprop, ConvTranspose forward = dgrad, and the
+    opposite direction for input gradients, wgrad for both;
+  * bias + activation are fused into the producing kernel's epilogue; BatchNorm statistics
+    are accumulated in the ConvTranspose epilogue (fp64 atomics) and the normalise + ReLU pass
+    is one streaming kernel; the LeakyReLU/ReLU backward of layer L is fused into the epilogue
+    of layer L+1's input-gradient kernel (mask = saved output of layer L);
+  * layers the tensor-core path does not cover (Cin = 3 first layer, Cout = 3 / 19 last layers,
+    the 1x1-input ConvTranspose) run on the generic SIMT kernels directly on the same buffers
+    (strided bf16 views) -- there is no torch / cuDNN fallback anywhere.
+
+Forward pre-hooks of the wrapped modules (legacy spectral_norm) are honoured: they run before
+the chain and the chain consumes ``module.weight`` (= weight_orig / sigma, an autograd tensor).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib as L
+from . import functional as Fn
+from . import tc
+from ._lib import ACT_NONE, call, ptr, stream, t4
+
+
+def precision():
+    return os.environ.get("EADGAN_PRECISION", "bf16")
+
+
+def _pow2(v):
+    return v > 0 and (v & (v - 1)) == 0
+
+
+class _Stage:
+    __slots__ = ("kind", "conv", "bn", "act", "stride", "pad", "r")
+
+    def __init__(self, kind, conv):
+        self.kind, self.conv, self.bn, self.act = kind, conv, None, (ACT_NONE, 0.0)
+        self.stride = conv.stride[0]
+        self.pad = conv.padding[0]
+        self.r = conv.kernel_size[0]
+
+
+def _compile(seq):
+    from . import nn as enn
+    mods = list(seq._modules.values())
+    stages, i = [], 0
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, enn.Conv2d):
+            kind = "conv"
+        elif isinstance(m, enn.ConvTranspose2d):
+            kind = "convT"
+        else:
+            return None
+        if (m.groups != 1 or m.dilation != (1, 1) or m.kernel_size[0] != m.kernel_size[1]
+                or m.stride[0] != m.stride[1] or m.padding[0] != m.padding[1] or m._forward_hooks
+                or m._backward_hooks or getattr(m, "padding_mode", "zeros") != "zeros"
+                or (kind == "convT" and m.output_padding != (0, 0))):
+            return None
+        st = _Stage(kind, m)
+        i += 1
+        if i < len(mods) and isinstance(mods[i], enn.BatchNorm2d) and enn._plain(mods[i]):
+            bn = mods[i]
+            if not (bn.affine and bn.track_running_stats) or bn.momentum is None:
+                return None
+            st.bn = bn
+            i += 1
+        if i < len(mods) and isinstance(mods[i], enn._Act) and enn._plain(mods[i]):
+            st.act = mods[i].act()
+            i += 1
+        stages.append(st)
+    if not stages or stages[-1].bn is not None:
+        return None
+    return stages
+
+
+def _plan(seq):
+    key = tuple(id(m) for m in seq._modules.values())
+    cached = seq.__dict__.get("_eadgan_plan")
+    if cached is None or cached[0] != key:
+        cached = (key, _compile(seq))
+        seq.__dict__["_eadgan_plan"] = cached
+    return cached[1]
+
+
 def try_run(seq, x):
-    return None
+    """Returns the Sequential's output, or None when the chain path does not apply."""
+    if precision() != "bf16" or not torch.is_tensor(x) or not x.is_cuda or x.dim() != 4 or x.dtype != torch.float32:
+        return None
+    stages = _plan(seq)
+    if stages is None:
+        return None
+    if any(st.bn is not None and not st.bn.training for st in stages):
+        return None  # eval-mode BN: per-op path
+    params = []
+    for st in stages:
+        for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
+            hook(st.conv, (x,))
+        params += [st.conv.weight, st.conv.bias]
+        if st.bn is not None:
+            st.bn.num_batches_tracked.add_(1)
+            params += [st.bn.weight, st.bn.bias]
+    return _ChainFn.apply(x, stages, *params)
+
+
+# ------------------------------------------------------------------------------------------
+class _Buf:
+    """an activation in one of the two formats: 'ext' fp32 NCHW tensor, 'pad' padded NHWC bf16."""
+    __slots__ = ("t", "fmt")
+
+    def __init__(self, t, fmt):
+        self.t, self.fmt = t, fmt
+
+    @property
+    def nchw(self):  # logical (n, c, h, w)
+        if self.fmt == "ext":
+            return tuple(self.t.shape)
+        n, hp, wp, c = self.t.shape
+        return (n, c, hp - 2, wp - 2)
+
+    def view(self):  # logical NCHW view usable with t4()
+        return self.t if self.fmt == "ext" else tc.interior(self.t)
+
+    def padded(self):
+        return self.t if self.fmt == "pad" else tc.to_padded(self.t)
+
+
+def _geom(st, in_shape):
+    """conv-view descriptor (always stated as the forward conv x[n,c,h,w] -> y[n,k,p,q])."""
+    w = st.conv.weight
+    r, s_, pad = st.r, st.stride, st.pad
+    if st.kind == "conv":
+        n, c, h, ww = in_shape
+        k = w.shape[0]
+        p = (h + 2 * pad - r) // s_ + 1
+        q = (ww + 2 * pad - r) // s_ + 1
+    else:
+        n, k, p, q = in_shape
+        c = w.shape[1]
+        h = (p - 1) * s_ - 2 * pad + r
+        ww = (q - 1) * s_ - 2 * pad + r
+    return L.ConvDesc(n, c, h, ww, k, r, r, p, q, s_, pad)
+
+
+def _tc_ok(d, direction):
+    if not (d.r == 4 and d.stride == 2 and d.pad == 1 and d.h == 2 * d.p and d.w == 2 * d.q):
+        return False
+    if not (_pow2(d.p) and _pow2(d.q)):
+        return False
+    if direction == "fprop":
+        return d.c % 32 == 0 and d.k % 32 == 0 and d.q <= 128
+    if direction == "dgrad":
+        return d.k % 64 == 0 and d.c % 32 == 0 and d.q <= 128
+    return (d.k % 128 == 0 or d.k == 64) and d.c % 32 == 0 and d.q <= 64  # wgrad
+
+
+def _chan_sums(buf, c):
+    """per-channel sum of a buffer in either format -> fp32 [c]"""
+    n, cc, h, w = buf.nchw
+    sums = torch.zeros(2 * c, device=buf.t.device, dtype=torch.float64)
+    d = t4(buf.view())
+    call("eadgan_bn_stats", C.byref(d), n, c, h, w, ptr(sums), stream())
+    return sums[:c].float()
+
+
+class _ChainFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, stages, *params):
+        st_ = stream()
+        dev = x.device
+        cur = _Buf(x.contiguous(), "ext")
+        saved = []
+        pi = 0
+        for si, st in enumerate(stages):
+            w, b = params[pi], params[pi + 1]
+            pi += 2
+            gamma = beta = None
+            if st.bn is not None:
+                gamma, beta = params[pi], params[pi + 1]
+                pi += 2
+            last = si == len(stages) - 1
+            d = _geom(st, cur.nchw)
+            direction = "fprop" if st.kind == "conv" else "dgrad"
+            out_shape = (d.n, d.k, d.p, d.q) if st.kind == "conv" else (d.n, d.c, d.h, d.w)
+            cout = out_shape[1]
+            epi_act = st.act if st.bn is None else (ACT_NONE, 0.0)
+            stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if st.bn is not None else None
+            wc = w.contiguous()
+            if _tc_ok(d, direction):
+                inp = _Buf(cur.padded(), "pad")
+                wpk = tc.pack_w(wc, None, direction)
+                fn = tc.fprop if st.kind == "conv" else tc.dgrad
+                out_t = fn(inp.t, wpk, b, cout, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats)
+                out = _Buf(out_t, "ext" if last else "pad")
+            else:
+                inp = cur
+                if last:
+                    out = _Buf(torch.empty(out_shape, device=dev, dtype=torch.float32), "ext")
+                else:
+                    out = _Buf(tc.alloc_padded(out_shape[0], out_shape[2], out_shape[3], cout, dev), "pad")
+                ind, outd = t4(inp.view()), t4(out.view())
+                call("eadgan_conv_fprop" if st.kind == "conv" else "eadgan_conv_dgrad", C.byref(d), C.byref(ind),
+                     ptr(wc), ptr(b), epi_act[0], float(epi_act[1]), C.byref(outd), None, ACT_NONE, 0.0, st_)
+                if stats is not None:
+                    call("eadgan_bn_stats", C.byref(outd), out_shape[0], cout, out_shape[2], out_shape[3],
+                         ptr(stats), st_)
+            rec = {"inp": inp, "d": d, "w": wc, "has_b": b is not None}
+            if st.bn is not None:
+                bn = st.bn
+                count = float(out_shape[0] * out_shape[2] * out_shape[3])
+                if Fn._allreduce_sum is not None:
+                    Fn._allreduce_sum(stats)
+                    count *= Fn._world_size
+                mean = torch.empty(cout, device=dev, dtype=torch.float32)
+                invstd = torch.empty(cout, device=dev, dtype=torch.float32)
+                call("eadgan_bn_finalize", ptr(stats), count, cout, float(bn.eps), float(bn.momentum), ptr(mean),
+                     ptr(invstd), ptr(bn.running_mean), ptr(bn.running_var), st_)
+                y = _Buf(tc.alloc_padded(out_shape[0], out_shape[2], out_shape[3], cout, dev), "pad")
+                xd, yd = t4(out.view()), t4(y.view())
+                call("eadgan_bn_apply", C.byref(xd), out_shape[0], cout, out_shape[2], out_shape[3], ptr(mean),
+                     ptr(invstd), ptr(gamma), ptr(beta), st.act[0], float(st.act[1]), C.byref(yd), st_)
+                rec.update(pre=out, mean=mean, invstd=invstd, gamma=gamma, beta=beta, count=count)
+                out = y
+            rec["y"] = out
+            saved.append(rec)
+            cur = out
+        # the returned tensor is saved through autograd (no ctx <-> output reference cycle)
+        saved[-1]["y"] = None
+        ctx.save_for_backward(cur.t)
+        ctx.stages, ctx.saved = stages, saved
+        return cur.t
+
+    @staticmethod
+    def backward(ctx, gout):
+        stages, saved = ctx.stages, ctx.saved
+        saved[-1]["y"] = _Buf(ctx.saved_tensors[0], "ext")
+        st_ = stream()
+        dev = gout.device
+        g = _Buf(gout.contiguous(), "ext")
+        g_masked = False
+        grads = []
+        for si in range(len(stages) - 1, -1, -1):
+            st, sv = stages[si], saved[si]
+            d = sv["d"]
+            cout = d.k if st.kind == "conv" else d.c
+            n, _, oh, ow = sv["y"].nchw if sv["y"] is not None else (0, 0, 0, 0)
+            dgamma = dbeta = None
+            # ---- 1. gradient w.r.t. the conv output (pre-BN / pre-activation) ----------------
+            if st.bn is not None:
+                sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+                gd, xd, yd = t4(g.view()), t4(sv["pre"].view()), t4(sv["y"].view())
+                call("eadgan_bn_bwd_reduce", C.byref(gd), C.byref(xd), C.byref(yd), n, cout, oh, ow, ptr(sv["mean"]),
+                     ptr(sv["invstd"]), ptr(sv["gamma"]), ptr(sv["beta"]), st.act[0], float(st.act[1]), ptr(sums), st_)
+                local = sums
+                if Fn._allreduce_sum is not None:
+                    local = sums.clone()
+                    Fn._allreduce_sum(sums)
+                call("eadgan_bn_bwd_apply", C.byref(gd), C.byref(xd), C.byref(yd), n, cout, oh, ow, ptr(sv["mean"]),
+                     ptr(sv["invstd"]), ptr(sv["gamma"]), ptr(sv["beta"]), st.act[0], float(st.act[1]), ptr(sums),
+                     float(sv["count"]), C.byref(gd), st_)  # in place: dz overwrites g
+                dbeta, dgamma = local[:cout].float(), local[cout:].float()
+                dz = g
+            elif st.act[0] != ACT_NONE and not g_masked:
+                if g.fmt != "ext" or sv["y"].fmt != "ext":
+                    raise RuntimeError("eadgan_b200.chain: unfused activation backward on a private buffer")
+                dz = _Buf(Fn.act_bwd(g.t, sv["y"].t, st.act[0], st.act[1]), "ext")
+            else:
+                dz = g
+            db = _chan_sums(dz, cout) if sv["has_b"] else None
+            # ---- 2. weight gradient ------------------------------------------------------------
+            x_big, dy_small = (sv["inp"], dz) if st.kind == "conv" else (dz, sv["inp"])
+            if _tc_ok(d, "wgrad"):
+                dw = tc.wgrad(x_big.padded(), dy_small.padded())
+            else:
+                dw = torch.zeros_like(sv["w"])
+                xd, dyd = t4(x_big.view()), t4(dy_small.view())
+                call("eadgan_conv_wgrad", C.byref(d), C.byref(xd), C.byref(dyd), ptr(dw), st_)
+            # ---- 3. input gradient ---------------------------------------------------------------
+            need_dx = si > 0 or ctx.needs_input_grad[0]
+            g_masked = False
+            if need_dx:
+                prev = stages[si - 1] if si > 0 else None
+                fuse = prev is not None and prev.bn is None and prev.act[0] != ACT_NONE
+                mask_act, mask_slope = (prev.act if fuse else (ACT_NONE, 0.0))
+                in_shape = sv["inp"].nchw
+                direction = "dgrad" if st.kind == "conv" else "fprop"
+                if _tc_ok(d, direction) and (not fuse or sv["inp"].fmt == "pad"):
+                    wpk = tc.pack_w(sv["w"], None, direction)
+                    fn = tc.dgrad if st.kind == "conv" else tc.fprop
+                    dx_t = fn(dz.padded(), wpk, None, in_shape[1], mask=sv["inp"].t if fuse else None,
+                              mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0))
+                    dx = _Buf(dx_t, "ext" if si == 0 else "pad")
+                else:
+                    if si > 0:
+                        dx = _Buf(tc.alloc_padded(in_shape[0], in_shape[2], in_shape[3], in_shape[1], dev), "pad")
+                    else:
+                        dx = _Buf(torch.empty(in_shape, device=dev, dtype=torch.float32), "ext")
+                    dzd, dxd = t4(dz.view()), t4(dx.view())
+                    md = t4(sv["inp"].view()) if fuse else None
+                    call("eadgan_conv_dgrad" if st.kind == "conv" else "eadgan_conv_fprop", C.byref(d), C.byref(dzd),
+                         ptr(sv["w"]), None, ACT_NONE, 0.0, C.byref(dxd), C.byref(md) if fuse else None, mask_act,
+                         float(mask_slope), st_)
+                g, g_masked = dx, fuse
+            stage_grads = [dw, db]
+            if st.bn is not None:
+                stage_grads += [dgamma, dbeta]
+            grads = stage_grads + grads
+        dx0 = g.t if ctx.needs_input_grad[0] else None
+        ctx.saved = None
+        return (dx0, None, *grads)

@@ -23,8 +23,11 @@ int eadgan_set_error(int code, const char* fmt, ...);
                               cudaGetErrorString(_e), __FILE__, __LINE__);              \
   } while (0)
 
+void eg_count_launch();
+
 #define EG_LAUNCH_CHECK(name)                                                           \
   do {                                                                                  \
+    eg_count_launch();                                                                  \
     cudaError_t _e = cudaGetLastError();                                                \
     if (_e != cudaSuccess)                                                              \
       return eadgan_set_error(EADGAN_ERR_CUDA, "launch of %s failed: %s", name,         \

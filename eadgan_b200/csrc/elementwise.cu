@@ -5,6 +5,8 @@
 // nn.Softmax / nn.Upsample in celebA/EAD-GAN_celebA.py:80-92,111-134,
 // dSprites/rp.py:67-183, MNIST/EAD-GAN_rpqmnxy.py:81-91,107,161.
 #include <stdarg.h>
+
+#include <atomic>
 #include <string.h>
 
 #include "common.cuh"
@@ -32,6 +34,10 @@ int eg_sm_count() {
   }
   return cached;
 }
+
+static std::atomic<long long> g_launches{0};
+void eg_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" int64_t eadgan_kernel_launches(void) { return (int64_t)g_launches.load(); }
 
 extern "C" const char* eadgan_last_error(void) { return g_err; }
 extern "C" int eadgan_version(void) { return EADGAN_VERSION; }

@@ -142,7 +142,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_step, m), denom));
 }
 
-__global__ void __launch_bounds__(256) adam_kernel(const AdamLaunch L, float beta1, float beta2, float eps,
+__global__ void __launch_bounds__(256) adam_kernel(const AdamLaunch L, float w1, float beta2, float w2, float eps,
                                                    float neg_step, float bc2_sqrt, float gscale) {
   int ti = 0;
   while (ti + 1 < L.t.count && (int)blockIdx.x >= L.blk_start[ti + 1]) ++ti;
@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamLaunch L, float bet
   const float* __restrict__ g = L.t.g[ti];
   float* __restrict__ m = L.t.m[ti];
   float* __restrict__ v = L.t.v[ti];
-  const float w1 = 1.f - beta1, w2 = 1.f - beta2;
   const bool al = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
                     reinterpret_cast<uintptr_t>(v)) & 15) == 0;
   if (al) {
@@ -251,7 +250,7 @@ extern "C" int eadgan_mi_bwd(const float* q, const float* c, const float* gout, 
   return 0;
 }
 
-extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, float beta1, float beta2, float eps,
+extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, double eps,
                                 double step_size, double bc2_sqrt, float grad_scale, void* stream) {
   EG_REQUIRE(t && t->count > 0 && t->count <= EADGAN_ADAM_MAX_TENSORS, EADGAN_ERR_INVALID,
              "adam_step: tensor count must be in [1, %d]", EADGAN_ADAM_MAX_TENSORS);
@@ -265,8 +264,10 @@ extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, float beta1, float
     blocks += (int)((t->numel[i] + ADAM_CHUNK - 1) / ADAM_CHUNK);
   }
   L.blk_start[t->count] = blocks;
-  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L, beta1, beta2, eps, (float)(-step_size),
-                                                        (float)bc2_sqrt, grad_scale);
+  // scalars are rounded to fp32 exactly where torch rounds its Python doubles: 1-beta1 and
+  // 1-beta2 are formed in double first (1 - 0.999 != 1.f - 0.999f)
+  adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
+                                                        (float)eps, (float)(-step_size), (float)bc2_sqrt, grad_scale);
   EG_LAUNCH_CHECK("adam_kernel");
   return 0;
 }

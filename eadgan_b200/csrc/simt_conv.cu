@@ -18,6 +18,9 @@ struct ConvArgs {
   eadgan_conv_desc d;
   eadgan_tensor4 a;  // gathered operand: x (fprop, wgrad) or dy (dgrad)
   eadgan_tensor4 o;  // output y / dx (fprop, dgrad) or the dense operand dy (wgrad)
+  eadgan_tensor4 mask;  // optional: output *= mask_act'(mask[n,ch,y,x]) (fused activation backward)
+  int mask_act;
+  float mask_slope;
   const float* w;
   const float* bias;
   float* dw;
@@ -147,6 +150,11 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
       float v = acc[i][j];
       if (P.bias) v += P.bias[nn];
       v = eg_act(v, P.act, P.slope);
+      if (P.mask_act != EADGAN_ACT_NONE) {
+        const float mv = eg_ld(P.mask.ptr, (int64_t)b * P.mask.sn + (int64_t)nn * P.mask.sc +
+                                               (int64_t)oy * P.mask.sh + (int64_t)ox * P.mask.sw, P.mask.dtype);
+        v *= eg_act_grad(mv, P.mask_act, P.mask_slope);
+      }
       eg_st(P.o.ptr, base + (int64_t)nn * P.o.sc, P.o.dtype, v);
     }
   }
@@ -301,11 +309,12 @@ int check_desc(const eadgan_conv_desc* d) {
 
 extern "C" int eadgan_conv_fprop(const eadgan_conv_desc* d, const eadgan_tensor4* x, const float* w,
                                  const float* bias, int act, float slope, const eadgan_tensor4* y,
-                                 void* stream) {
+                                 const eadgan_tensor4* mask, int mask_act, float mask_slope, void* stream) {
   if (int e = check_desc(d)) return e;
   EG_REQUIRE(x && y && x->ptr && y->ptr && w, EADGAN_ERR_INVALID, "conv_fprop: NULL tensor");
   ConvArgs P{};
   P.d = *d; P.a = *x; P.o = *y; P.w = w; P.bias = bias; P.act = act; P.slope = slope;
+  if (mask && mask_act != EADGAN_ACT_NONE) { P.mask = *mask; P.mask_act = mask_act; P.mask_slope = mask_slope; }
   P.M = d->n * d->p * d->q; P.N = d->k; P.K = d->c * d->r * d->s;
   dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN);
   conv_gemm_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(P);
@@ -315,11 +324,12 @@ extern "C" int eadgan_conv_fprop(const eadgan_conv_desc* d, const eadgan_tensor4
 
 extern "C" int eadgan_conv_dgrad(const eadgan_conv_desc* d, const eadgan_tensor4* dy, const float* w,
                                  const float* bias, int act, float slope, const eadgan_tensor4* dx,
-                                 void* stream) {
+                                 const eadgan_tensor4* mask, int mask_act, float mask_slope, void* stream) {
   if (int e = check_desc(d)) return e;
   EG_REQUIRE(dy && dx && dy->ptr && dx->ptr && w, EADGAN_ERR_INVALID, "conv_dgrad: NULL tensor");
   ConvArgs P{};
   P.d = *d; P.a = *dy; P.o = *dx; P.w = w; P.bias = bias; P.act = act; P.slope = slope;
+  if (mask && mask_act != EADGAN_ACT_NONE) { P.mask = *mask; P.mask_act = mask_act; P.mask_slope = mask_slope; }
   P.M = d->n * d->h * d->w; P.N = d->c; P.K = d->k * d->r * d->s;
   dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN);
   conv_gemm_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(P);

@@ -92,7 +92,7 @@ class _ConvFn(torch.autograd.Function):
         y = torch.empty((n, k) if two_d else (n, k, p, q), device=x.device, dtype=torch.float32)
         xd, yd = t4(x), t4(y)
         call("eadgan_conv_fprop", C.byref(d), C.byref(xd), ptr(w), ptr(b), act, float(slope),
-             C.byref(yd), stream())
+             C.byref(yd), None, ACT_NONE, 0.0, stream())
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
         ctx.cfg = (d, act, slope, b is not None)
         return y
@@ -109,7 +109,7 @@ class _ConvFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             dxd = t4(dx)
             call("eadgan_conv_dgrad", C.byref(d), C.byref(dzd), ptr(w), None, ACT_NONE, 0.0,
-                 C.byref(dxd), stream())
+                 C.byref(dxd), None, ACT_NONE, 0.0, stream())
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(w)
             xd = t4(x)
@@ -138,7 +138,7 @@ class _ConvTFn(torch.autograd.Function):
         y = torch.empty((n, c, h, ww), device=x.device, dtype=torch.float32)
         xd, yd = t4(x), t4(y)
         call("eadgan_conv_dgrad", C.byref(d), C.byref(xd), ptr(w), ptr(b), act, float(slope),
-             C.byref(yd), stream())
+             C.byref(yd), None, ACT_NONE, 0.0, stream())
         ctx.save_for_backward(x, w, y if act != ACT_NONE else None)
         ctx.cfg = (d, act, slope, b is not None)
         return y
@@ -155,7 +155,7 @@ class _ConvTFn(torch.autograd.Function):
             dx = torch.empty_like(x)
             dxd = t4(dx)
             call("eadgan_conv_fprop", C.byref(d), C.byref(dzd), ptr(w), None, ACT_NONE, 0.0,
-                 C.byref(dxd), stream())
+                 C.byref(dxd), None, ACT_NONE, 0.0, stream())
         if ctx.needs_input_grad[1]:
             dw = torch.zeros_like(w)
             xd = t4(x)

@@ -74,6 +74,8 @@ const char* eadgan_last_error(void);
 int eadgan_version(void);
 /* number of SMs of the current device (grid sizing on the host side) */
 int eadgan_sm_count(void);
+/* total number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t eadgan_kernel_launches(void);
 
 /* ------------------------------------------------------------------------- */
 /* Generic fp32-accumulate SIMT implicit-GEMM convolution (any r,s,stride,pad) */
@@ -83,14 +85,16 @@ int eadgan_sm_count(void);
 /* 165-183; MNIST/EAD-GAN_rpqmnxy.py:77-91,105-124,141-163.                    */
 /* nn.Linear(i,o) is the r=s=h=w=1 case.                                      */
 /* ------------------------------------------------------------------------- */
-/* y = act(conv(x, w) + bias) */
+/* y = act(conv(x, w) + bias) [* mask_act'(mask)]   -- mask: optional tensor of y's shape holding a
+ * saved post-activation output; multiplies the result by that activation's derivative (fused
+ * activation backward when this call computes an input gradient).  mask may be NULL. */
 int eadgan_conv_fprop(const eadgan_conv_desc* d, const eadgan_tensor4* x, const float* w,
                       const float* bias, int act, float slope, const eadgan_tensor4* y,
-                      void* stream);
+                      const eadgan_tensor4* mask, int mask_act, float mask_slope, void* stream);
 /* dx = act(conv_transpose(dy, w) + bias)   (bias/act used when this IS a ConvTranspose2d forward) */
 int eadgan_conv_dgrad(const eadgan_conv_desc* d, const eadgan_tensor4* dy, const float* w,
                       const float* bias, int act, float slope, const eadgan_tensor4* dx,
-                      void* stream);
+                      const eadgan_tensor4* mask, int mask_act, float mask_slope, void* stream);
 /* dw[k,c,r,s] (+)= sum_{n,p,q} dy * patch(x); dw must be zeroed by the caller unless accumulate */
 int eadgan_conv_wgrad(const eadgan_conv_desc* d, const eadgan_tensor4* x, const eadgan_tensor4* dy,
                       float* dw, void* stream);
@@ -248,7 +252,7 @@ typedef struct {
 } eadgan_adam_tensors;
 /* step_size = lr / (1-beta1^t), bc2_sqrt = sqrt(1-beta2^t), both computed in double on the
  * host exactly as torch does; grad_scale multiplies g on load (1/world_size for DP sums). */
-int eadgan_adam_step(const eadgan_adam_tensors* t, float beta1, float beta2, float eps,
+int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, double eps,
                      double step_size, double bc2_sqrt, float grad_scale, void* stream);
 
 /* fill / scale helpers used by the host layer (buffer zeroing stays on our stream) */

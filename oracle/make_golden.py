@@ -1,0 +1,56 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.json by executing the UNMODIFIED reference
+scripts (oracle/ref_runner.py) in this container:  python -m oracle.make_golden
+
+The reference ships no tests or golden vectors, so these fixtures -- the
+reference's own outputs on seeded synthetic inputs with seeded random-init weights -- are what
+pins oracle/torch_oracle.py (and, through it, the CUDA path).  Each fixture stores the losses
+and a fingerprint (sum, L2 norm, abs-max, 8 probes) of every gradient tensor seen by every
+``optimizer.step()`` and of every parameter after it.
+"""
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_runner as R  # noqa: E402
+from oracle import torch_oracle as O  # noqa: E402
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def fingerprint_log(log):
+    out = []
+    for e in log:
+        out.append({"lr": e["lr"],
+                    "grads": [None if g is None else O.summarize(g) for g in e["grads"]],
+                    "params_after": [O.summarize(p) for p in e["params_after"]]})
+    return out
+
+
+def make_celeba(B=4, seed=0):
+    imgs = O.synth_celeba_images(B, seed)
+    ns, log = R.run_script("celeba", [(imgs, torch.zeros(B, dtype=torch.long))], argv=["--batch_size", str(B)],
+                           seed=seed)
+    return {"config": "celeba", "batch": B, "seed": seed, "torch": torch.__version__,
+            "source": "celebA/EAD-GAN_celebA.py executed by oracle/ref_runner.py",
+            "losses": {"g_loss": ns["g_loss"].item(), "d_loss": ns["d_loss"].item(),
+                       "info_loss": ns["info_loss"].item()},
+            "phases": fingerprint_log(log)}
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    for name, fn in (("celeba_b4_seed0", lambda: make_celeba(4, 0)), ("celeba_b6_seed3", lambda: make_celeba(6, 3))):
+        g = fn()
+        with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
+            json.dump(g, f, indent=1)
+        print(name, g["losses"])
+
+
+if __name__ == "__main__":
+    main()

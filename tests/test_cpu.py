@@ -1,0 +1,178 @@
+"""CPU suite (-m "not gpu"): the oracle against the golden vectors generated from the reference, the
+oracle against the reference itself when /root/reference is present, the host-side mirror (state_dict
+layout, constructor parity, no-CPU-fallback errors), and the C-ABI library (loads, exports every
+symbol include/eadgan.h declares)."""
+import ctypes
+import json
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+
+warnings.filterwarnings("ignore")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def _close(a, b, rtol, atol=1e-9):
+    return abs(a - b) <= atol + rtol * max(abs(a), abs(b))
+
+
+def _check_fp(t, fp, rtol):
+    from oracle.torch_oracle import summarize
+    s = summarize(t)
+    scale = max(fp["absmax"], 1e-12)
+    assert abs(s["l2"] - fp["l2"]) <= rtol * max(fp["l2"], 1e-12) + 1e-9
+    assert abs(s["absmax"] - fp["absmax"]) <= rtol * scale + 1e-9
+    for a, b in zip(s["probe"], fp["probe"]):
+        assert abs(a - b) <= rtol * scale + 1e-9
+
+
+@pytest.mark.parametrize("name", ["celeba_b4_seed0", "celeba_b6_seed3"])
+def test_oracle_reproduces_reference_golden(name):
+    """oracle/torch_oracle.py (the restatement that travels to the GPU box) vs fixtures produced by
+    executing celebA/EAD-GAN_celebA.py itself (oracle/make_golden.py)."""
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    B, seed = g["batch"], g["seed"]
+    torch.set_num_threads(8)
+    st = O.build_celeba(seed=seed)
+    rec = O.step_celeba(st, O.synth_celeba_images(B, seed), O.sample_celeba(np.random.RandomState(seed), B))
+    for k, v in g["losses"].items():
+        assert _close(rec["losses"][k], v, 1e-5), (k, rec["losses"][k], v)
+    assert len(rec["phases"]) == len(g["phases"]) == 3
+    # phase G and D start from identical weights: tight.  The info phase follows two Adam steps whose
+    # first update is ~ lr*sign(g), so thread-count / ISA dependent rounding
+    # can flip signs of near-zero gradients: gradients are still tight, post-step weights looser.
+    for ph, gph, (rt_g, rt_p) in zip(rec["phases"], g["phases"], [(1e-4, 1e-4), (1e-4, 1e-4), (2e-3, 2e-3)]):
+        assert len(ph["grads"]) == len(gph["grads"])
+        for t, fp in zip(ph["grads"], gph["grads"]):
+            _check_fp(t, fp, rt_g)
+        for t, fp in zip(ph["params_after"], gph["params_after"]):
+            _check_fp(t, fp, rt_p)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
+def test_oracle_classes_equal_reference_classes():
+    """key-for-key, bit-for-bit equality of the restated modules with the AST-extracted reference classes."""
+    from oracle import ref_runner as R, torch_oracle as O
+    ns = R.extract_defs("celeba")
+    torch.manual_seed(5)
+    G_ref, D_ref = ns["Generator"](), ns["Discriminator"]()
+    torch.manual_seed(5)
+    G, D = O.CelebAGenerator(), O.CelebADiscriminator()
+    for a, b in ((G_ref, G), (D_ref, D)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        for k in sa:
+            assert sa[k].shape == sb[k].shape and sa[k].dtype == sb[k].dtype and torch.equal(sa[k], sb[k]), k
+    z, lab, code = torch.randn(3, 200), torch.eye(10)[:3], torch.rand(3, 8)
+    assert torch.equal(G_ref(z, lab, code), G(z, lab, code))
+    x = torch.randn(3, 3, 64, 64)
+    for a, b in zip(D_ref(x), D(x)):
+        assert torch.equal(a, b)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
+def test_reference_affine_glue_matches():
+    import importlib.util
+    import sys
+    from oracle import torch_oracle as O
+    from eadgan_b200 import affine
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        spec = importlib.util.spec_from_file_location("ref_utils_rpqxy", "/root/reference/celebA/utils_rpqxy.py")
+        U = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(U)
+        torch.manual_seed(0)
+        c1, c2 = torch.rand(9, 8) * 2 - 1, torch.rand(9, 8) * 2 - 1
+        m_ref = U.get_matrix(c1[:, :5])
+        r_ref = U.affine_regularzier(c1, c2)
+    finally:
+        torch.Tensor.cuda = saved
+    for impl_m, impl_r in ((O.celeba_get_matrix, O.celeba_affine_regularizer),
+                           (affine.celeba_matrix, affine.celeba_relative_code)):
+        assert (impl_m(c1[:, :5]) - m_ref).abs().max() <= 1e-6
+        assert (impl_r(c1, c2) - r_ref).abs().max() <= 1e-4
+
+
+def test_product_modules_mirror_reference_layout():
+    """eadgan_b200 modules: same keys / shapes / seeded init as the stock-torch oracle, both directions of
+    load_state_dict, legacy spectral-norm metadata."""
+    from eadgan_b200.steps.celeba import Discriminator, Generator
+    from oracle import torch_oracle as O
+    torch.manual_seed(11)
+    G, D = Generator(), Discriminator()
+    torch.manual_seed(11)
+    Gr, Dr = O.CelebAGenerator(), O.CelebADiscriminator()
+    for a, b in ((G, Gr), (D, Dr)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+        assert sa._metadata == sb._metadata
+        b.load_state_dict(sa)
+        a.load_state_dict(sb)
+    assert sum(p.numel() for p in G.parameters()) == 14591619
+    assert sum(p.numel() for p in D.parameters()) == 11329427
+    names = [type(m).__name__ for m in G.modules()]
+    assert any("Conv" in n for n in names) and any("BatchNorm" in n for n in names)  # weights_init_normal keys
+
+
+def test_no_cpu_fallback():
+    import eadgan_b200.nn as enn
+    from eadgan_b200.optim import Adam
+    with pytest.raises(RuntimeError, match="no CPU"):
+        enn.Conv2d(3, 4, 4, 2, 1)(torch.zeros(1, 3, 8, 8))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        enn.BCELoss()(torch.rand(4), torch.ones(4))
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        Adam([p], lr=1e-3).step()
+
+
+def test_patch_rebinds_and_restores():
+    import eadgan_b200
+    import eadgan_b200.nn as enn
+    stock = torch.nn.Conv2d
+    eadgan_b200.patch()
+    try:
+        assert torch.nn.Conv2d is enn.Conv2d and torch.optim.Adam is eadgan_b200.optim.Adam
+        assert torch.nn.utils.spectral_norm is enn.spectral_norm
+        m = torch.nn.utils.spectral_norm(torch.nn.Conv2d(3, 8, 4, 2, 1))
+        assert list(m.state_dict().keys()) == ["bias", "weight_orig", "weight_u", "weight_v"]
+    finally:
+        eadgan_b200.unpatch()
+    assert torch.nn.Conv2d is stock
+
+
+def test_c_abi_exports_every_declared_symbol():
+    from eadgan_b200 import _lib
+    import __graft_entry__ as ge
+    ge.build()
+    hdr = open(os.path.join(ROOT, "include", "eadgan.h")).read()
+    declared = set(re.findall(r"\b(eadgan_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"eadgan_status", "eadgan_dtype", "eadgan_act"}
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(lib, n)]
+    assert not missing, missing
+    assert declared == set(_lib.EXPORTED), declared ^ set(_lib.EXPORTED)
+    assert lib.eadgan_version() == 100
+
+
+def test_sass_is_blackwell_native():
+    """tcgen05.mma / tcgen05.ld / TMA must be in the built library (UTC*MMA / LDTM / UTMALDG SASS)."""
+    import shutil
+    import subprocess
+    from eadgan_b200 import _lib
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
