@@ -34,7 +34,8 @@ class ConvDesc(C.Structure):
 class TcDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32),
                 ("k", C.c_int32), ("act", C.c_int32), ("slope", C.c_float),
-                ("out_f32_nchw", C.c_int32), ("want_stats", C.c_int32), ("mask_mode", C.c_int32)]
+                ("out_f32_nchw", C.c_int32), ("want_stats", C.c_int32), ("c_real", C.c_int32),
+                ("mask_mode", C.c_int32)]
 
 
 class AdamTensors(C.Structure):
@@ -53,8 +54,12 @@ _PROTOS = {
     "eadgan_conv_dgrad": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _T4, _I, _F, _P],
     "eadgan_conv_wgrad": [C.POINTER(ConvDesc), _T4, _T4, _P, _P],
     "eadgan_channel_sum": [_T4, _I, _I, _I, _I, _P, _P],
-    "eadgan_tc_pack_w_fprop": [_P, _P, _I, _I, _P, _P],
-    "eadgan_tc_pack_w_dgrad": [_P, _P, _I, _I, _P, _P],
+    "eadgan_tc_pack_w_fprop": [_P, _P, _I, _I, _I, _P, _P],
+    "eadgan_tc_pack_w_dgrad": [_P, _P, _I, _I, _I, _P, _P],
+    "eadgan_tc_dense_pack": [_P, _I, _I, _I, _I, _P, _P],
+    "eadgan_tc_dense_gather": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "eadgan_tc_dense_scatter": [_P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _P],
+    "eadgan_tc_dense_wgrad": [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P],
     "eadgan_tc_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
     "eadgan_tc_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
     "eadgan_tc_wgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, C.c_size_t, _P],
@@ -91,6 +96,7 @@ _SPECIAL = {
     "eadgan_sm_count": ([], C.c_int),
     "eadgan_kernel_launches": ([], C.c_int64),
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
+    "eadgan_tc_dense_wgrad_workspace": ([_I, _I], C.c_size_t),
 }
 EXPORTED = sorted(list(_PROTOS) + list(_SPECIAL))
 
@@ -134,6 +140,18 @@ def _flops(name, args):
     return 0
 
 
+def _shape_tag(args):
+    try:
+        d = args[0]._obj
+    except (AttributeError, IndexError):
+        return ""
+    if isinstance(d, ConvDesc):
+        return f"[n{d.n} c{d.c} h{d.h} k{d.k} r{d.r} s{d.stride}]"
+    if isinstance(d, TcDesc):
+        return f"[n{d.n} c{d.c} h{d.h} k{d.k}]"
+    return ""
+
+
 def profile_start():
     """time every C-ABI call with CUDA events on the launching stream (bench.py roofline leg)."""
     global _prof
@@ -162,7 +180,7 @@ def call(name, *args):
         e0.record()
         rc = getattr(lib(), name)(*args)
         e1.record()
-        _prof.append((name, _flops(name, args), e0, e1))
+        _prof.append((name + _shape_tag(args), _flops(name, args), e0, e1))
     else:
         rc = getattr(lib(), name)(*args)
     launches += 1

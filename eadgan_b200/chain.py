@@ -154,16 +154,41 @@ def _geom(st, in_shape):
     return L.ConvDesc(n, c, h, ww, k, r, r, p, q, s_, pad)
 
 
+def _calloc(d):
+    """big-map channel count the tensor-core kernels run with: d.c, or 32 when the layer has fewer than
+    32 real channels (the 1- / 3-channel image layers are zero-padded to 32), or None if unsupported."""
+    if d.c % 32 == 0:
+        return d.c
+    return 32 if d.c < 32 else None
+
+
 def _tc_ok(d, direction):
     if not (d.r == 4 and d.stride == 2 and d.pad == 1 and d.h == 2 * d.p and d.w == 2 * d.q):
         return False
-    if not (_pow2(d.p) and _pow2(d.q)):
+    if not (_pow2(d.p) and _pow2(d.q)) or _calloc(d) is None:
         return False
     if direction == "fprop":
-        return d.c % 32 == 0 and d.k % 32 == 0 and d.q <= 128
+        return d.k % 32 == 0 and d.q <= 128
     if direction == "dgrad":
-        return d.k % 64 == 0 and d.c % 32 == 0 and d.q <= 128
-    return (d.k % 128 == 0 or d.k == 64) and d.c % 32 == 0 and d.q <= 64  # wgrad
+        return d.k % 64 == 0 and d.q <= 128
+    return (d.k % 128 == 0 or d.k == 64) and d.q <= 64  # wgrad
+
+
+def _impl(st, d, last):
+    """which kernel family runs the forward of this stage."""
+    unit = d.r == 4 and d.stride == 1 and d.pad == 0 and d.h == 4 and d.w == 4 and d.p == 1 and d.q == 1
+    plain = st.bn is None and st.act[0] == ACT_NONE
+    if unit and plain and d.c % 128 == 0:
+        if st.kind == "convT" and d.k <= 256 and not last:
+            return "dense_T"
+        if st.kind == "conv" and d.k <= 32 and last:
+            return "dense_C"
+    direction = "fprop" if st.kind == "conv" else "dgrad"
+    if _tc_ok(d, direction):
+        if _calloc(d) != d.c and st.kind == "convT" and not (last and st.bn is None):
+            return "simt"  # zero-padded OUTPUT channels are only supported for an fp32 NCHW result
+        return "tc"
+    return "simt"
 
 
 def _chan_sums(buf, c):
@@ -173,6 +198,10 @@ def _chan_sums(buf, c):
     d = t4(buf.view())
     call("eadgan_bn_stats", C.byref(d), n, c, h, w, ptr(sums), stream())
     return sums[:c].float()
+
+
+def _r64(v):
+    return (v + 63) // 64 * 64
 
 
 class _ChainFn(torch.autograd.Function):
@@ -198,11 +227,28 @@ class _ChainFn(torch.autograd.Function):
             epi_act = st.act if st.bn is None else (ACT_NONE, 0.0)
             stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if st.bn is not None else None
             wc = w.contiguous()
-            if _tc_ok(d, direction):
+            impl = _impl(st, d, last)
+            rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl}
+            if impl == "dense_T":      # 1x1 -> 4x4 ConvTranspose: batch GEMM, scatter epilogue
+                a = tc.pad_rows(cur.t.reshape(d.n, d.k), _r64(d.k))
+                out = _Buf(tc.dense_scatter(a, tc.dense_pack(wc, _r64(d.k), False), b, d.c), "pad")
+                inp = cur
+                rec["a"] = a
+            elif impl == "dense_C":    # 4x4 -> 1x1 Conv head: batch GEMM, gather prologue
                 inp = _Buf(cur.padded(), "pad")
-                wpk = tc.pack_w(wc, None, direction)
-                fn = tc.fprop if st.kind == "conv" else tc.dgrad
-                out_t = fn(inp.t, wpk, b, cout, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats)
+                o = tc.dense_gather(inp.t, tc.dense_pack(wc, 32, True), b, d.k)
+                out = _Buf(o.view(d.n, d.k, 1, 1), "ext")
+            elif impl == "tc":
+                ca = _calloc(d)
+                if st.kind == "conv":
+                    inp = _Buf(cur.t if cur.fmt == "pad" else tc.to_padded(cur.t, ca), "pad")
+                    wpk = tc.pack_w(wc, None, "fprop", ca)
+                    out_t = tc.fprop(inp.t, wpk, b, cout, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats)
+                else:
+                    inp = _Buf(cur.padded(), "pad")
+                    wpk = tc.pack_w(wc, None, "dgrad", ca)
+                    out_t = tc.dgrad(inp.t, wpk, b, ca, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats,
+                                     c_real=d.c if ca != d.c else 0)
                 out = _Buf(out_t, "ext" if last else "pad")
             else:
                 inp = cur
@@ -216,7 +262,7 @@ class _ChainFn(torch.autograd.Function):
                 if stats is not None:
                     call("eadgan_bn_stats", C.byref(outd), out_shape[0], cout, out_shape[2], out_shape[3],
                          ptr(stats), st_)
-            rec = {"inp": inp, "d": d, "w": wc, "has_b": b is not None}
+            rec["inp"] = inp
             if st.bn is not None:
                 bn = st.bn
                 count = float(out_shape[0] * out_shape[2] * out_shape[3])
@@ -253,9 +299,9 @@ class _ChainFn(torch.autograd.Function):
         grads = []
         for si in range(len(stages) - 1, -1, -1):
             st, sv = stages[si], saved[si]
-            d = sv["d"]
+            d, impl = sv["d"], sv["impl"]
             cout = d.k if st.kind == "conv" else d.c
-            n, _, oh, ow = sv["y"].nchw if sv["y"] is not None else (0, 0, 0, 0)
+            n, _, oh, ow = sv["y"].nchw
             dgamma = dbeta = None
             # ---- 1. gradient w.r.t. the conv output (pre-BN / pre-activation) ----------------
             if st.bn is not None:
@@ -279,39 +325,65 @@ class _ChainFn(torch.autograd.Function):
             else:
                 dz = g
             db = _chan_sums(dz, cout) if sv["has_b"] else None
-            # ---- 2. weight gradient ------------------------------------------------------------
-            x_big, dy_small = (sv["inp"], dz) if st.kind == "conv" else (dz, sv["inp"])
-            if _tc_ok(d, "wgrad"):
-                dw = tc.wgrad(x_big.padded(), dy_small.padded())
-            else:
-                dw = torch.zeros_like(sv["w"])
-                xd, dyd = t4(x_big.view()), t4(dy_small.view())
-                call("eadgan_conv_wgrad", C.byref(d), C.byref(xd), C.byref(dyd), ptr(dw), st_)
-            # ---- 3. input gradient ---------------------------------------------------------------
+            prev = stages[si - 1] if si > 0 else None
             need_dx = si > 0 or ctx.needs_input_grad[0]
-            g_masked = False
-            if need_dx:
-                prev = stages[si - 1] if si > 0 else None
-                fuse = prev is not None and prev.bn is None and prev.act[0] != ACT_NONE
-                mask_act, mask_slope = (prev.act if fuse else (ACT_NONE, 0.0))
-                in_shape = sv["inp"].nchw
-                direction = "dgrad" if st.kind == "conv" else "fprop"
-                if _tc_ok(d, direction) and (not fuse or sv["inp"].fmt == "pad"):
-                    wpk = tc.pack_w(sv["w"], None, direction)
-                    fn = tc.dgrad if st.kind == "conv" else tc.fprop
-                    dx_t = fn(dz.padded(), wpk, None, in_shape[1], mask=sv["inp"].t if fuse else None,
-                              mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0))
-                    dx = _Buf(dx_t, "ext" if si == 0 else "pad")
+            fuse = need_dx and prev is not None and prev.bn is None and prev.act[0] != ACT_NONE
+            mask_act, mask_slope = (prev.act if fuse else (ACT_NONE, 0.0))
+            in_shape = (d.n, d.c, d.h, d.w) if st.kind == "conv" else (d.n, d.k, d.p, d.q)
+            dx = None
+            # ---- 2./3. weight gradient and input gradient -----------------------------------------
+            if impl == "dense_T":
+                dw = tc.dense_wgrad(sv["a"], dz.padded(), d.k)
+            elif impl == "dense_C":
+                a = tc.pad_rows(dz.t.reshape(d.n, d.k), 64)
+                dw = tc.dense_wgrad(a, sv["inp"].t, d.k)
+                if need_dx and (si > 0) and (not fuse or sv["inp"].fmt == "pad"):
+                    dx = _Buf(tc.dense_scatter(a, tc.dense_pack(sv["w"], 64, False), None, d.c,
+                                               mask=sv["inp"].t if fuse else None, mask_act=mask_act,
+                                               slope=mask_slope), "pad")
+            else:
+                ca = _calloc(d) if impl == "tc" else d.c
+                x_big, dy_small = (sv["inp"], dz) if st.kind == "conv" else (dz, sv["inp"])
+                if impl == "tc" and _tc_ok(d, "wgrad"):
+                    xb = x_big.t if x_big.fmt == "pad" else tc.to_padded(x_big.t, ca)
+                    if st.kind == "convT" and ca != d.c:
+                        dz = _Buf(xb, "pad")  # reuse the channel-padded copy for the input gradient below
+                        x_big = dz
+                    dw = tc.wgrad(xb, dy_small.padded(), c_real=d.c if ca != d.c else 0)
                 else:
-                    if si > 0:
-                        dx = _Buf(tc.alloc_padded(in_shape[0], in_shape[2], in_shape[3], in_shape[1], dev), "pad")
-                    else:
-                        dx = _Buf(torch.empty(in_shape, device=dev, dtype=torch.float32), "ext")
-                    dzd, dxd = t4(dz.view()), t4(dx.view())
-                    md = t4(sv["inp"].view()) if fuse else None
-                    call("eadgan_conv_dgrad" if st.kind == "conv" else "eadgan_conv_fprop", C.byref(d), C.byref(dzd),
-                         ptr(sv["w"]), None, ACT_NONE, 0.0, C.byref(dxd), C.byref(md) if fuse else None, mask_act,
-                         float(mask_slope), st_)
+                    dw = torch.zeros_like(sv["w"])
+                    xd, dyd = t4(x_big.view()), t4(dy_small.view())
+                    call("eadgan_conv_wgrad", C.byref(d), C.byref(xd), C.byref(dyd), ptr(dw), st_)
+                if need_dx:
+                    direction = "dgrad" if st.kind == "conv" else "fprop"
+                    tc_dx = impl == "tc" and _tc_ok(d, direction) and (not fuse or sv["inp"].fmt == "pad")
+                    if tc_dx and ca != d.c and st.kind == "conv" and si > 0:
+                        tc_dx = False  # zero-padded result channels need the fp32 NCHW epilogue (si == 0)
+                    if tc_dx:
+                        wpk = tc.pack_w(sv["w"], None, direction, ca)
+                        if st.kind == "conv":
+                            dx_t = tc.dgrad(dz.padded(), wpk, None, ca, mask=sv["inp"].t if fuse else None,
+                                            mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0),
+                                            c_real=d.c if ca != d.c else 0)
+                        else:
+                            dzp = dz.t if dz.fmt == "pad" else tc.to_padded(dz.t, ca)
+                            dx_t = tc.fprop(dzp, wpk, None, in_shape[1], mask=sv["inp"].t if fuse else None,
+                                            mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0))
+                        dx = _Buf(dx_t, "ext" if si == 0 else "pad")
+            if need_dx and dx is None:   # generic SIMT input gradient on the same buffers
+                if si > 0:
+                    dx = _Buf(tc.alloc_padded(in_shape[0], in_shape[2], in_shape[3], in_shape[1], dev), "pad")
+                else:
+                    dx = _Buf(torch.empty(in_shape, device=dev, dtype=torch.float32), "ext")
+                dzv = dz.view()
+                if dzv.shape[1] != cout:
+                    dzv = dzv[:, :cout]
+                dzd, dxd = t4(dzv), t4(dx.view())
+                md = t4(sv["inp"].view()) if fuse else None
+                call("eadgan_conv_dgrad" if st.kind == "conv" else "eadgan_conv_fprop", C.byref(d), C.byref(dzd),
+                     ptr(sv["w"]), None, ACT_NONE, 0.0, C.byref(dxd), C.byref(md) if fuse else None, mask_act,
+                     float(mask_slope), st_)
+            if need_dx:
                 g, g_masked = dx, fuse
             stage_grads = [dw, db]
             if st.bn is not None:

@@ -120,6 +120,13 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
       }
     }
     __syncthreads();
+    // two-level accumulation: each 16-deep k tile is summed on its own, then added to the running
+    // total -- rounding error grows with sqrt(K/16) instead of sqrt(K) (K is up to 16384 here)
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kl = 0; kl < BK; ++kl) {
       const float4 a4 = *reinterpret_cast<const float4*>(&As[kl][tx * 4]);
@@ -129,8 +136,12 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 
@@ -225,6 +236,11 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const ConvArgs P) {
       Qs[ml][col] = qv;
     }
     __syncthreads();
+    float part[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) part[i][j] = 0.f;
 #pragma unroll
     for (int kl = 0; kl < BK; ++kl) {
       const float4 a4 = *reinterpret_cast<const float4*>(&Ps[kl][tx * 4]);
@@ -234,8 +250,12 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const ConvArgs P) {
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        for (int j = 0; j < 4; ++j) part[i][j] = fmaf(av[i], bv[j], part[i][j]);
     }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
   }
 #pragma unroll

@@ -155,7 +155,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
 // ------------------------------------------------------------------------------------
 // kernel parameters
 // ------------------------------------------------------------------------------------
-enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2 };
+enum { MODE_GEMM = 0, MODE_FPROP = 1, MODE_DGRAD = 2, MODE_DENSE_GATHER = 3 };
 
 struct TcParams {
   int mode;
@@ -175,6 +175,8 @@ struct TcParams {
   const __nv_bfloat16* mask;
   double* stats;
   int gemm_m, gemm_n;  // MODE_GEMM extents
+  int n_store;         // real output channels (<= N_total; the rest is zero padding of the operand)
+  int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
 };
 
 constexpr int BLOCK_M = 128;
@@ -249,6 +251,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (P.mode == MODE_GEMM) {
           tma_load_2d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
           tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+        } else if (P.mode == MODE_DENSE_GATHER) {
+          // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]
+          const int qi = kb % P.qblocks, tap = kb / P.qblocks;
+          tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (tap & 3), 1 + (tap >> 2), m_tile * BLOCK_M);
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
         } else if (P.mode == MODE_FPROP) {
           const int qi = kb % P.qblocks, t = kb / P.qblocks;
           const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
@@ -298,10 +305,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int64_t out_off = 0;     // element offset of (pixel, channel n0) in the output
     int64_t ch_stride = 1;   // element stride between channels in the output
     int64_t mask_off = 0;
-    if (P.mode == MODE_GEMM) {
+    int bias_base = n0;      // channel index of accumulator column 0 of this tile
+    bool f32_out;
+    if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) {
       const int m = m_tile * BLOCK_M + row;
       valid = m < P.gemm_m;
-      out_off = (int64_t)m * P.gemm_n + n0;
+      if (P.mode == MODE_GEMM && P.dense_C > 0) {
+        // scatter: GEMM column n = tap * C + ch  ->  padded map [m][1+ky][1+kx][ch]
+        const int tap = n0 / P.dense_C, ch0 = n0 - tap * P.dense_C;
+        out_off = (((int64_t)m * 6 + 1 + (tap >> 2)) * 6 + 1 + (tap & 3)) * P.dense_C + ch0;
+        mask_off = out_off;
+        bias_base = ch0;
+        f32_out = false;
+      } else {
+        out_off = (int64_t)m * P.n_store + n0;
+        f32_out = true;
+      }
     } else {
       const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
       const int b = b0 + bl;
@@ -311,23 +330,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
       const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
       mask_off = pad_off;
-      if (P.out_f32_nchw) {
-        out_off = (((int64_t)b * P.N_total + n0) * P.OH + oy) * P.OW + ox;
+      f32_out = P.out_f32_nchw != 0;
+      if (f32_out) {
+        out_off = (((int64_t)b * P.n_store + n0) * P.OH + oy) * P.OW + ox;
         ch_stride = (int64_t)P.OH * P.OW;
       } else {
         out_off = pad_off;
       }
     }
-    const bool f32_out = (P.mode == MODE_GEMM) || P.out_f32_nchw;
 
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      const bool ch_ok = (P.mode != MODE_GEMM) || (n0 + c0 < P.gemm_n);
+      const int n_left = P.n_store - (n0 + c0);  // real channels remaining from this column on
       if (P.bias) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += __ldg(&P.bias[n0 + c0 + j]);
+        for (int j = 0; j < 32; ++j)
+          if (j < n_left || P.dense_C > 0) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
       }
       if (P.want_stats) {
         // per-channel sum / sum of squares over the 32 pixels of this warp (butterfly),
@@ -351,7 +371,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 0] = (double)s1[0];
         stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 1] = (double)s2[0];
       }
-      if (valid && ch_ok) {
+      if (valid && (n_left > 0 || P.dense_C > 0)) {
         if (P.act != EADGAN_ACT_NONE) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = eg_act(v[j], P.act, P.slope);
@@ -372,13 +392,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         if (f32_out) {
           float* op = reinterpret_cast<float*>(P.out) + out_off + (int64_t)c0 * ch_stride;
-          if (ch_stride == 1) {
+          if (ch_stride == 1 && n_left >= 32 && (P.n_store & 3) == 0) {
 #pragma unroll
             for (int g = 0; g < 8; ++g)
               *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) op[(int64_t)j * ch_stride] = v[j];
+            for (int j = 0; j < 32; ++j)
+              if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
           }
         } else {
           __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + out_off + c0;
@@ -399,7 +420,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       // combine the four warps' partials: 128 epilogue threads, one named barrier
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int et = threadIdx.x - 64;  // 0..127
-      for (int ch = et; ch < BLOCK_N; ch += 128) {
+      for (int ch = et; ch < BLOCK_N && n0 + ch < P.n_store; ch += 128) {
         double a = 0.0, b2 = 0.0;
 #pragma unroll
         for (int w = 0; w < 4; ++w) { a += stat_smem[(w * BLOCK_N + ch) * 2]; b2 += stat_smem[(w * BLOCK_N + ch) * 2 + 1]; }
@@ -427,6 +448,7 @@ struct WgParams {
   int steps_per_split;
   int Ktot;             // 16*c
   float* partial;       // [splits][k][16c]
+  int dense;            // 1: "pixels" are batch rows; A boxes from a [n][Mp] matrix, B boxes from [n,6,6,C]
 };
 
 template <int BLOCK_N>  // BLOCK_N columns of kk per tile (multiple of 64)
@@ -479,17 +501,29 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         uint8_t* sa = smem + stage * C::STAGE_BYTES;
         uint8_t* sb = sa + C::A_B;
         mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        const int b0 = (st / P.tiles_y) * P.Tb;
-        const int y0 = (st % P.tiles_y) * P.Th;
+        if (P.dense) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h)
-          tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+          for (int h = 0; h < 2; ++h)
+            tma_load_2d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, st * 64);
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 64; ++i) {
-          const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
-          const int qi = nb % P.qblocks, t = nb / P.qblocks;
-          const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-          tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
+          for (int i = 0; i < BLOCK_N / 64; ++i) {
+            const int nb = kk_tile * (BLOCK_N / 64) + i;
+            const int qi = nb % P.qblocks, tap = nb / P.qblocks;  // tap = ky*4+kx
+            tma_load_4d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
+          }
+        } else {
+          const int b0 = (st / P.tiles_y) * P.Tb;
+          const int y0 = (st % P.tiles_y) * P.Th;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i) {
+            const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
+            const int qi = nb % P.qblocks, t = nb / P.qblocks;
+            const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+            tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
+          }
         }
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
@@ -547,7 +581,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 // sum split partials and permute GEMM column order (a,b,dy,dx,c) -> dw[ko][c][ky][kx]
 // block = (ko, 64-channel group); coalesced reads of 16 x 64-float runs, one 4 KB write
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int k, int c,
-                                                           float* __restrict__ dw) {
+                                                           int c_real, float* __restrict__ dw) {
   __shared__ float tile[16][65];
   const int ko = blockIdx.y, c0 = blockIdx.x * 64;
   const int Ktot = 16 * c;
@@ -566,7 +600,44 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   __syncthreads();
   for (int e = threadIdx.x; e < 64 * 16; e += 256) {
     const int cl = e / 16, tp = e % 16;
-    if (c0 + cl < c) dw[((int64_t)ko * c + c0 + cl) * 16 + tp] = tile[tp][cl];
+    if (c0 + cl < c_real) dw[((int64_t)ko * c_real + c0 + cl) * 16 + tp] = tile[tp][cl];
+  }
+}
+
+// dense layers: partial[m][tap*C + ch] (tap = ky*4+kx) -> dw[m][ch][ky][kx]
+__global__ void __launch_bounds__(256) dense_wgrad_reduce_kernel(const float* __restrict__ partial, int m_pad, int C,
+                                                                 float* __restrict__ dw) {
+  __shared__ float tile[16][65];
+  const int m = blockIdx.y, c0 = blockIdx.x * 64;
+  for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+    const int tap = e / 64, cl = e % 64;
+    tile[tap][cl] = partial[(int64_t)m * 16 * C + (int64_t)tap * C + c0 + cl];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const int cl = e / 16, tp = e % 16;
+    dw[((int64_t)m * C + c0 + cl) * 16 + tp] = tile[tp][cl];
+  }
+}
+
+// dense weight packs from w[m][ch][tap] (m_real x C x 16, fp32):
+//   rows_major = 1:  out[m][tap*C + ch]   (m padded to m_pad rows)      -- B operand of the gather GEMM
+//   rows_major = 0:  out[tap*C + ch][m]   (m padded to m_pad columns)   -- B operand of the scatter GEMM
+__global__ void dense_pack_kernel(const float* __restrict__ w, int m_real, int m_pad, int C, int rows_major,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int64_t total = (int64_t)m_pad * 16 * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int m, tap, ch;
+    if (rows_major) {
+      m = (int)(i / (16 * C));
+      const int r = (int)(i - (int64_t)m * 16 * C);
+      tap = r / C; ch = r - tap * C;
+    } else {
+      const int64_t r = i / m_pad;
+      m = (int)(i - r * m_pad);
+      tap = (int)(r / C); ch = (int)(r - (int64_t)tap * C);
+    }
+    out[i] = __float2bfloat16_rn(m < m_real ? w[((int64_t)m * C + ch) * 16 + tap] : 0.f);
   }
 }
 
@@ -574,8 +645,8 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
 // weight packing
 // ------------------------------------------------------------------------------------
 // Wf[ko][((a*2+b)*2+dy)*2c + dx*c + ci] = w[ko][ci][2a+dy][2b+dx] / sigma
-__global__ void pack_w_fprop_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c,
-                                    __nv_bfloat16* __restrict__ out) {
+__global__ void pack_w_fprop_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c_real,
+                                    int c, __nv_bfloat16* __restrict__ out) {
   const float inv = sigma ? 1.f / *sigma : 1.f;
   const int64_t total = (int64_t)k * 16 * c;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -585,12 +656,12 @@ __global__ void pack_w_fprop_kernel(const float* __restrict__ w, const float* __
     const int dx = rem / c, ci = rem - dx * c;
     const int dy = t3 & 1, bt = (t3 >> 1) & 1, at = t3 >> 2;
     const int ky = 2 * at + dy, kx = 2 * bt + dx;
-    out[i] = __float2bfloat16_rn(w[(((int64_t)ko * c + ci) * 4 + ky) * 4 + kx] * inv);
+    out[i] = __float2bfloat16_rn(ci < c_real ? w[(((int64_t)ko * c_real + ci) * 4 + ky) * 4 + kx] * inv : 0.f);
   }
 }
 // Wd[(py*2+px)*c + co][(ty*2+tx)*k + ki] = w[ki][co][ky(py,ty)][kx(px,tx)] / sigma
-__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c,
-                                    __nv_bfloat16* __restrict__ out) {
+__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c_real,
+                                    int c, __nv_bfloat16* __restrict__ out) {
   const float inv = sigma ? 1.f / *sigma : 1.f;
   const int64_t total = (int64_t)4 * c * 4 * k;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -601,7 +672,7 @@ __global__ void pack_w_dgrad_kernel(const float* __restrict__ w, const float* __
     const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
     const int ky = py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2);
     const int kx = px == 0 ? (tx == 0 ? 1 : 3) : (tx == 0 ? 0 : 2);
-    out[i] = __float2bfloat16_rn(w[(((int64_t)ki * c + co) * 4 + ky) * 4 + kx] * inv);
+    out[i] = __float2bfloat16_rn(co < c_real ? w[(((int64_t)ki * c_real + co) * 4 + ky) * 4 + kx] * inv : 0.f);
   }
 }
 
@@ -715,24 +786,26 @@ int check_tc(const eadgan_tc_desc* d, const char* who) {
 
 }  // namespace
 
-extern "C" int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c, void* w_packed,
+extern "C" int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c_real, int c, void* w_packed,
                                       void* stream) {
-  EG_REQUIRE(w && w_packed && k > 0 && c > 0, EADGAN_ERR_INVALID, "tc_pack_w_fprop: bad arguments");
+  EG_REQUIRE(w && w_packed && k > 0 && c > 0 && c_real > 0 && c_real <= c, EADGAN_ERR_INVALID,
+             "tc_pack_w_fprop: bad arguments");
   const int64_t total = (int64_t)k * 16 * c;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
-  pack_w_fprop_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c, (__nv_bfloat16*)w_packed);
+  pack_w_fprop_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c, (__nv_bfloat16*)w_packed);
   EG_LAUNCH_CHECK("pack_w_fprop_kernel");
   return 0;
 }
 
-extern "C" int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c, void* w_packed,
+extern "C" int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c_real, int c, void* w_packed,
                                       void* stream) {
-  EG_REQUIRE(w && w_packed && k > 0 && c > 0, EADGAN_ERR_INVALID, "tc_pack_w_dgrad: bad arguments");
+  EG_REQUIRE(w && w_packed && k > 0 && c > 0 && c_real > 0 && c_real <= c, EADGAN_ERR_INVALID,
+             "tc_pack_w_dgrad: bad arguments");
   const int64_t total = (int64_t)k * 16 * c;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
-  pack_w_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c, (__nv_bfloat16*)w_packed);
+  pack_w_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c, (__nv_bfloat16*)w_packed);
   EG_LAUNCH_CHECK("pack_w_dgrad_kernel");
   return 0;
 }
@@ -752,7 +825,7 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = d->c; P.qblocks = 2 * d->c / 64; P.nkb = 8 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
-  P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k;
   EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_fprop: mask_mode without mask");
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_fprop: want_stats without stats");
   CUtensorMap ma, mb;
@@ -778,6 +851,9 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
   P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+  P.n_store = (d->c_real > 0 && d->c_real < d->c) ? d->c_real : d->c;
+  EG_REQUIRE(P.n_store == d->c || d->out_f32_nchw, EADGAN_ERR_UNSUPPORTED,
+             "tc_dgrad: zero-padded output channels (c_real < c) need out_f32_nchw");
   EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_dgrad: mask_mode without mask");
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_dgrad: want_stats without stats");
   CUtensorMap ma, mb;
@@ -858,7 +934,8 @@ extern "C" int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const
     default: rc = launch_wgrad<256>(mdy, mx, PK, grid, st); break;
   }
   if (rc) return rc;
-  wgrad_reduce_kernel<<<dim3((d->c + 63) / 64, d->k), 256, 0, st>>>(P.partial, splits, k_pad, d->c, dw);
+  const int c_real = (d->c_real > 0 && d->c_real < d->c) ? d->c_real : d->c;
+  wgrad_reduce_kernel<<<dim3((d->c + 63) / 64, d->k), 256, 0, st>>>(P.partial, splits, k_pad, d->c, c_real, dw);
   EG_LAUNCH_CHECK("wgrad_reduce_kernel");
   return 0;
 }
@@ -870,10 +947,94 @@ extern "C" int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f
   const int bn = pick_bn(n);
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: N=%d must be a multiple of 32", n);
   TcParams P{};
-  P.mode = MODE_GEMM; P.nkb = kk / 64; P.gemm_m = m; P.gemm_n = n; P.out = c_f32; P.N_total = n;
+  P.mode = MODE_GEMM; P.nkb = kk / 64; P.gemm_m = m; P.gemm_n = n; P.out = c_f32; P.N_total = n; P.n_store = n;
   CUtensorMap ma, mb;
   if (int e = map_matrix(&ma, a_bf16, m, kk, 128)) return e;
   if (int e = map_matrix(&mb, b_bf16, n, kk, bn)) return e;
   dim3 grid((m + 127) / 128, n / bn, 1);
   return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------
+// "dense" 4x4 <-> 1x1 layers as GEMMs over the batch:
+//   ConvTranspose2d(m, C, 4, 1, 0) on a 1x1 input (celebA/EAD-GAN_celebA.py:76) and
+//   Conv2d(C, m, 4, 1, 0) on a 4x4 input (the D/Q head, celebA/EAD-GAN_celebA.py:122)
+// ------------------------------------------------------------------------------------
+namespace {
+int map_pad6(CUtensorMap* m, const void* base, int n, int C, int rows_box) {
+  const uint64_t dims[4] = {(uint64_t)C, 6, 6, (uint64_t)n};
+  const uint64_t st[3] = {(uint64_t)C * 2, (uint64_t)6 * C * 2, (uint64_t)36 * C * 2};
+  const uint32_t box[4] = {64, 1, 1, (uint32_t)rows_box};
+  return encode_map(m, base, 4, dims, st, box);
+}
+}  // namespace
+
+extern "C" int eadgan_tc_dense_pack(const float* w, int m_real, int m_pad, int C, int rows_major, void* out,
+                                    void* stream) {
+  EG_REQUIRE(w && out && m_real > 0 && m_pad >= m_real && C > 0, EADGAN_ERR_INVALID, "tc_dense_pack: bad arguments");
+  const int64_t total = (int64_t)m_pad * 16 * C;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
+  dense_pack_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, m_real, m_pad, C, rows_major, (__nv_bfloat16*)out);
+  EG_LAUNCH_CHECK("dense_pack_kernel");
+  return 0;
+}
+
+// out[b][j] (fp32, j < m_real) = bias[j] + sum_{tap,c} Y[b][tap][c] * Wp[j][tap*C + c]
+extern "C" int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, const float* bias, float* out, int n,
+                                      int C, int m_real, void* stream) {
+  EG_REQUIRE(y_pad && w_rows && out && n > 0 && m_real > 0, EADGAN_ERR_INVALID, "tc_dense_gather: bad arguments");
+  EG_REQUIRE(C % 64 == 0 && m_real <= 32, EADGAN_ERR_UNSUPPORTED, "tc_dense_gather: needs C%%64==0 and m<=32");
+  TcParams P{};
+  P.mode = MODE_DENSE_GATHER; P.qblocks = C / 64; P.nkb = 16 * P.qblocks; P.gemm_m = n; P.gemm_n = 32;
+  P.N_total = 32; P.n_store = m_real; P.bias = bias; P.out = out;
+  CUtensorMap ma, mb;
+  if (int e = map_pad6(&ma, y_pad, n, C, 128)) return e;
+  if (int e = map_matrix(&mb, w_rows, 32, (uint64_t)16 * C, 32)) return e;
+  dim3 grid((n + 127) / 128, 1, 1);
+  return dispatch_conv(32, ma, mb, P, grid, (cudaStream_t)stream);
+}
+
+// Out[b][1+ky][1+kx][ch] (padded NHWC bf16) = (bias[ch] + sum_j A[b][j] * Wp[tap*C + ch][j]) * mask'(.)
+extern "C" int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, const float* bias, void* out_pad,
+                                       const void* mask, int mask_act, float slope, int n, int C, int m_pad,
+                                       void* stream) {
+  EG_REQUIRE(a_bf16 && w_cols && out_pad && n > 0, EADGAN_ERR_INVALID, "tc_dense_scatter: bad arguments");
+  EG_REQUIRE(C % 128 == 0 && m_pad % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_dense_scatter: needs C%%128==0, m_pad%%64==0");
+  TcParams P{};
+  P.mode = MODE_GEMM; P.nkb = m_pad / 64; P.gemm_m = n; P.gemm_n = 16 * C; P.N_total = 16 * C; P.n_store = 16 * C;
+  P.dense_C = C; P.bias = bias; P.out = out_pad; P.mask = (const __nv_bfloat16*)mask; P.mask_mode = mask ? mask_act : 0;
+  P.slope = slope;
+  CUtensorMap ma, mb;
+  if (int e = map_matrix(&ma, a_bf16, n, m_pad, 128)) return e;
+  if (int e = map_matrix(&mb, w_cols, (uint64_t)16 * C, m_pad, 128)) return e;
+  dim3 grid((n + 127) / 128, 16 * C / 128, 1);
+  return dispatch_conv(128, ma, mb, P, grid, (cudaStream_t)stream);
+}
+
+extern "C" size_t eadgan_tc_dense_wgrad_workspace(int C, int m_pad) {
+  const int mp = ((m_pad + 127) / 128) * 128;
+  return (size_t)mp * 16 * C * sizeof(float);
+}
+
+// dw[j][ch][ky][kx] (fp32, j < m_real) = sum_b A[b][j] * Y[b][1+ky][1+kx][ch]
+extern "C" int eadgan_tc_dense_wgrad(const void* a_bf16, const void* y_pad, float* dw, void* workspace,
+                                     size_t ws_bytes, int n, int C, int m_real, int m_pad, void* stream) {
+  EG_REQUIRE(a_bf16 && y_pad && dw && workspace && n > 0, EADGAN_ERR_INVALID, "tc_dense_wgrad: bad arguments");
+  EG_REQUIRE(C % 64 == 0 && m_pad % 64 == 0 && m_real <= m_pad, EADGAN_ERR_UNSUPPORTED,
+             "tc_dense_wgrad: needs C%%64==0 and m_pad%%64==0");
+  const int mp = ((m_pad + 127) / 128) * 128;
+  EG_REQUIRE(ws_bytes >= (size_t)mp * 16 * C * sizeof(float), EADGAN_ERR_WORKSPACE, "tc_dense_wgrad: workspace too small");
+  WgParams P{};
+  P.dense = 1; P.n = n; P.k = mp; P.c = C; P.qblocks = C / 64; P.Ktot = 16 * C;
+  P.steps_total = (n + 63) / 64; P.steps_per_split = P.steps_total; P.partial = (float*)workspace;
+  CUtensorMap ma, mx;
+  if (int e = map_matrix(&ma, a_bf16, n, m_pad, 64)) return e;
+  if (int e = map_pad6(&mx, y_pad, n, C, 64)) return e;
+  dim3 grid(P.Ktot / 256, mp / 128, 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_wgrad<256>(ma, mx, P, grid, st)) return rc;
+  dense_wgrad_reduce_kernel<<<dim3(C / 64, m_real), 256, 0, st>>>(P.partial, mp, C, dw);
+  EG_LAUNCH_CHECK("dense_wgrad_reduce_kernel");
+  return 0;
 }

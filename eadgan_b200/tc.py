@@ -21,13 +21,22 @@ def interior(xp):
     return xp.permute(0, 3, 1, 2)[:, :, 1:hp - 1, 1:wp - 1]
 
 
-def to_padded(x):
-    """fp32/bf16 NCHW tensor -> padded NHWC bf16 (copy4 kernel)."""
+def to_padded(x, c_alloc=None):
+    """fp32/bf16 NCHW tensor -> padded NHWC bf16 (copy4 kernel); channels zero-padded to c_alloc."""
     n, c, h, w = x.shape
-    xp = alloc_padded(n, h, w, c, x.device)
-    src, dst = t4(x), t4(interior(xp))
+    xp = alloc_padded(n, h, w, c_alloc or c, x.device)
+    src, dst = t4(x), t4(interior(xp)[:, :c])
     call("eadgan_copy4", C.byref(src), C.byref(dst), n, c, h, w, stream())
     return xp
+
+
+def pad_rows(x2d, m_pad):
+    """fp32 [n, m] -> bf16 [n, m_pad] (zero padded columns)."""
+    n, m = x2d.shape
+    out = torch.zeros((n, m_pad), device=x2d.device, dtype=torch.bfloat16)
+    src, dst = t4(x2d), t4(out[:, :m])
+    call("eadgan_copy4", C.byref(src), C.byref(dst), n, m, 1, 1, stream())
+    return out
 
 
 def from_padded(xp, dtype=torch.float32):
@@ -38,18 +47,20 @@ def from_padded(xp, dtype=torch.float32):
     return out
 
 
-def pack_w(w, sigma=None, direction="fprop"):
-    """fp32 [k, c, 4, 4] -> bf16 GEMM operand ([k,16c] for fprop, [4c,4k] for dgrad), / sigma."""
+def pack_w(w, sigma=None, direction="fprop", c_alloc=None):
+    """fp32 [k, c, 4, 4] -> bf16 GEMM operand ([k,16c] for fprop, [4c,4k] for dgrad), / sigma;
+    the c axis is zero-padded to c_alloc."""
     k, c = w.shape[0], w.shape[1]
+    ca = c_alloc or c
     assert tuple(w.shape[2:]) == (4, 4)
-    out = torch.empty(k * 16 * c, device=w.device, dtype=torch.bfloat16)
+    out = torch.empty(k * 16 * ca, device=w.device, dtype=torch.bfloat16)
     call("eadgan_tc_pack_w_fprop" if direction == "fprop" else "eadgan_tc_pack_w_dgrad",
-         ptr(w.contiguous()), ptr(sigma), k, c, ptr(out), stream())
+         ptr(w.contiguous()), ptr(sigma), k, c, ca, ptr(out), stream())
     return out
 
 
-def _desc(n, c, h, w, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, want_stats=False, mask_mode=0):
-    return L.TcDesc(n, c, h, w, k, act, float(slope), int(out_f32_nchw), int(want_stats), int(mask_mode))
+def _desc(n, c, h, w, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, want_stats=False, mask_mode=0, c_real=0):
+    return L.TcDesc(n, c, h, w, k, act, float(slope), int(out_f32_nchw), int(want_stats), int(c_real), int(mask_mode))
 
 
 def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
@@ -66,13 +77,13 @@ def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=No
 
 
 def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
-          out=None):
-    """small map yp [n,p+2,q+2,k] -> big map [n,2p+2,2q+2,c] (or fp32 NCHW [n,c,2p,2q])."""
+          out=None, c_real=0):
+    """small map yp [n,p+2,q+2,k] -> big map [n,2p+2,2q+2,c] (or fp32 NCHW [n,c_real or c,2p,2q])."""
     n, pp, qp, k = yp.shape
     h, w = 2 * (pp - 2), 2 * (qp - 2)
-    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode)
+    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode, c_real)
     if out is None:
-        out = (torch.empty((n, c, h, w), device=yp.device, dtype=torch.float32) if out_f32_nchw
+        out = (torch.empty((n, c_real or c, h, w), device=yp.device, dtype=torch.float32) if out_f32_nchw
                else alloc_padded(n, h, w, c, yp.device))
     call("eadgan_tc_dgrad", C.byref(d), ptr(yp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), stream())
     return out
@@ -81,20 +92,59 @@ def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=No
 _ws_cache = {}
 
 
-def wgrad(xp, yp):
-    """dw[k,c,4,4] fp32 from the big map xp and the small map yp (both padded NHWC bf16)."""
+def _workspace(need, device):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(need, device=device, dtype=torch.uint8)
+        _ws_cache[key] = ws
+    return ws
+
+
+def dense_pack(w, m_pad, rows_major):
+    """w viewed as [m][C][16] -> bf16 [m_pad][16C] (rows_major) or [16C][m_pad]."""
+    m, Cc = w.shape[0], w.shape[1]
+    out = torch.empty(m_pad * 16 * Cc, device=w.device, dtype=torch.bfloat16)
+    call("eadgan_tc_dense_pack", ptr(w.contiguous()), m, m_pad, Cc, 1 if rows_major else 0, ptr(out), stream())
+    return out
+
+
+def dense_gather(yp, w_rows, bias, m_real):
+    n, _, _, Cc = yp.shape
+    out = torch.empty((n, m_real), device=yp.device, dtype=torch.float32)
+    call("eadgan_tc_dense_gather", ptr(yp), ptr(w_rows), ptr(bias), ptr(out), n, Cc, m_real, stream())
+    return out
+
+
+def dense_scatter(a, w_cols, bias, Cc, mask=None, mask_act=0, slope=0.0):
+    n, m_pad = a.shape
+    out = alloc_padded(n, 4, 4, Cc, a.device)
+    call("eadgan_tc_dense_scatter", ptr(a), ptr(w_cols), ptr(bias), ptr(out), ptr(mask), int(mask_act), float(slope),
+         n, Cc, m_pad, stream())
+    return out
+
+
+def dense_wgrad(a, yp, m_real):
+    n, m_pad = a.shape
+    Cc = yp.shape[3]
+    need = L.lib().eadgan_tc_dense_wgrad_workspace(Cc, m_pad)
+    ws = _workspace(need, a.device)
+    dw = torch.empty((m_real, Cc, 4, 4), device=a.device, dtype=torch.float32)
+    call("eadgan_tc_dense_wgrad", ptr(a), ptr(yp), ptr(dw), ptr(ws), C.c_size_t(ws.numel()), n, Cc, m_real, m_pad,
+         stream())
+    return dw
+
+
+def wgrad(xp, yp, c_real=0):
+    """dw[k,c_real or c,4,4] fp32 from the big map xp and the small map yp (both padded NHWC bf16)."""
     n, hp, wp, c = xp.shape
     k = yp.shape[3]
-    d = _desc(n, c, hp - 2, wp - 2, k)
+    d = _desc(n, c, hp - 2, wp - 2, k, c_real=c_real)
     need = L.lib().eadgan_tc_workspace_bytes(C.byref(d), 2)
     if need == 0:
         raise RuntimeError(f"tc wgrad: unsupported geometry n={n} c={c} h={hp - 2} k={k}")
-    key = (xp.device, torch.cuda.current_stream().cuda_stream)
-    ws = _ws_cache.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.empty(need, device=xp.device, dtype=torch.uint8)
-        _ws_cache[key] = ws
-    dw = torch.empty((k, c, 4, 4), device=xp.device, dtype=torch.float32)
+    ws = _workspace(need, xp.device)
+    dw = torch.empty((k, c_real or c, 4, 4), device=xp.device, dtype=torch.float32)
     call("eadgan_tc_wgrad", C.byref(d), ptr(xp), ptr(yp), ptr(dw), ptr(ws), C.c_size_t(ws.numel()), stream())
     return dw
 

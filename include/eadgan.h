@@ -118,6 +118,9 @@ typedef struct {
   int32_t out_f32_nchw; /* 1: write the result as dense fp32 NCHW instead of padded NHWC bf16 */
   int32_t want_stats;   /* 1: accumulate per-channel sum / sum-of-squares of the pre-activation
                               output into fp64 stats[2*C] (BatchNorm statistics fused in the epilogue) */
+  int32_t c_real;       /* 0 or c: all big-map channels are real.  0 < c_real < c: channels >= c_real of the
+                              big map are zero padding (the 3-channel image layers run with c = 32); weights
+                              are given / returned as [k, c_real, 4, 4] */
   int32_t mask_mode;    /* eadgan_act kind A != NONE: multiply the result by A'(mask), mask being the
                               saved padded NHWC bf16 post-activation tensor of the output's shape
                               (activation backward fused into the dgrad epilogue); 0 = off */
@@ -125,10 +128,10 @@ typedef struct {
 
 /* weight repacks (fp32 [k,c,4,4] -> bf16 GEMM operand layouts); weights are divided by
  * *sigma for spectral-normalised layers (pointer to a device float, or NULL for 1) */
-int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c, void* w_packed,
-                           void* stream);
-int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c, void* w_packed,
-                           void* stream);
+int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c_real, int c,
+                           void* w_packed, void* stream);
+int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c_real, int c,
+                           void* w_packed, void* stream);
 size_t eadgan_tc_workspace_bytes(const eadgan_tc_desc* d, int direction);
 int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const void* w_packed,
                     const float* bias, void* y, const void* mask, double* stats, void* stream);
@@ -141,6 +144,26 @@ int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const void* dy_p
  * and the 1x1-input ConvTranspose2d(218,1024,4,1,0) of celebA/EAD-GAN_celebA.py:76) */
 int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f32, int m, int n, int kk,
                    void* stream);
+
+/* "dense" 4x4 <-> 1x1 layers as batch GEMMs on the same tcgen05 mainloop:
+ * nn.ConvTranspose2d(218,1024,4,1,0) on the 1x1 latent (celebA/EAD-GAN_celebA.py:76) and the D/Q head
+ * nn.Conv2d(1024,19,4,1,0) on the 4x4 map (celebA/EAD-GAN_celebA.py:122).  The weight is always viewed
+ * as w[m][ch][tap] (m = 218 latent dims, or 19 head outputs; tap = ky*4+kx), the map as padded
+ * NHWC bf16 [n,6,6,C].
+ *   pack   : rows_major=1 -> bf16 [m_pad][16*C] ; rows_major=0 -> bf16 [16*C][m_pad]
+ *   gather : out[n][m_real] fp32 = bias + Y . w           (head forward)
+ *   scatter: Y[n,6,6,C] bf16 = (bias + A . w) * mask'      (ConvT forward; head input-gradient)
+ *   wgrad  : dw[m_real][C][4][4] fp32 = A^T . Y            (both weight gradients) */
+int eadgan_tc_dense_pack(const float* w, int m_real, int m_pad, int C, int rows_major, void* out,
+                         void* stream);
+int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, const float* bias, float* out, int n,
+                           int C, int m_real, void* stream);
+int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, const float* bias, void* out_pad,
+                            const void* mask, int mask_act, float slope, int n, int C, int m_pad,
+                            void* stream);
+size_t eadgan_tc_dense_wgrad_workspace(int C, int m_pad);
+int eadgan_tc_dense_wgrad(const void* a_bf16, const void* y_pad, float* dw, void* workspace,
+                          size_t ws_bytes, int n, int C, int m_real, int m_pad, void* stream);
 
 /* ------------------------------------------------------------------------- */
 /* layout / dtype conversion between module-boundary and private buffers      */

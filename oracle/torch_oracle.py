@@ -78,7 +78,7 @@ def celeba_affine_regularizer(real_code, trans_code):
     y = (rel[:, 1, 2] * torch.cos(th) - rel[:, 0, 2] * torch.sin(th)) / q
     # celebA/utils_rpqxy.py:41-55 (inverse rescale)
     out = torch.stack((th / np.pi * 9, (p - 1) / 0.2, (q - 1) / 0.2, x / 0.1, y / 0.1), dim=1)
-    return out.float()
+    return out.to(real_code.dtype)  # the reference's .float() (:116); dtype-preserving so an fp64 referee run works
 
 
 def stn(img, theta23, padding_mode="border"):
@@ -186,6 +186,7 @@ def step_celeba(st, imgs, draws, record=True):
     code = draws["code"].to(dev, dt)
     labels = draws["labels"].to(dev)
     label_input = one_hot(labels, 10, z)
+    imgs = imgs.to(dt)
     A = celeba_get_matrix(code[:, :5])                      # :325
     scaled = stn(imgs, A[:, 0:2])                           # :327
     rec = {"phases": []}

@@ -121,3 +121,72 @@ def test_sigma_scaled_pack(cuda):
     ref = TF.conv2d(x, _bf(w / 2.5), None, stride=2, padding=1)
     out = tc.fprop(tc.to_padded(x), tc.pack_w(w, sigma, "fprop"), None, 128, out_f32_nchw=True)
     assert rel_err(out, ref) <= 2e-3
+
+
+def test_channel_padded_image_layers(cuda):
+    """3-channel image layers run with the big map zero-padded to 32 channels (c_real = 3)."""
+    from eadgan_b200 import tc
+    from eadgan_b200._lib import ACT_TANH
+    torch.manual_seed(6)
+    n = 5
+    # Conv2d(3,128,4,2,1) forward / wgrad / input-gradient
+    x = _bf(torch.randn(n, 3, 64, 64, device=cuda))
+    w = _bf(torch.randn(128, 3, 4, 4, device=cuda) * 0.1)
+    b = torch.randn(128, device=cuda)
+    xp = tc.to_padded(x, 32)
+    ref = TF.conv2d(x, w, b, stride=2, padding=1)
+    out = tc.fprop(xp, tc.pack_w(w, None, "fprop", 32), b, 128, out_f32_nchw=True)
+    assert rel_err(out, ref) <= 2e-3
+    dy = _bf(torch.randn(n, 128, 32, 32, device=cuda))
+    wz = torch.zeros_like(w).requires_grad_()
+    xr = x.clone().requires_grad_()
+    gw = torch.autograd.grad(TF.conv2d(x, wz, None, stride=2, padding=1), wz, dy)[0]
+    gx = torch.autograd.grad(TF.conv2d(xr, w, None, stride=2, padding=1), xr, dy)[0]
+    dyp = tc.to_padded(dy)
+    assert rel_err(tc.wgrad(xp, dyp, c_real=3), gw) <= 2e-3
+    dx = tc.dgrad(dyp, tc.pack_w(w, None, "dgrad", 32), None, 32, out_f32_nchw=True, c_real=3)
+    assert dx.shape == (n, 3, 64, 64) and rel_err(dx, gx) <= 2e-3
+    # ConvTranspose2d(128,3,4,2,1) + bias + tanh forward
+    bt = torch.randn(3, device=cuda)
+    reft = torch.tanh(TF.conv_transpose2d(dy, w, bt, stride=2, padding=1))
+    outt = tc.dgrad(dyp, tc.pack_w(w, None, "dgrad", 32), bt, 32, ACT_TANH, out_f32_nchw=True, c_real=3)
+    assert rel_err(outt, reft) <= 2e-3
+
+
+@pytest.mark.parametrize("n", [8, 130, 200])
+def test_dense_layers(cuda, n):
+    """ConvTranspose2d(218,1024,4,1,0) on 1x1 and Conv2d(1024,19,4,1,0) on 4x4 as batch GEMMs."""
+    from eadgan_b200 import tc
+    from eadgan_b200._lib import ACT_LRELU
+    torch.manual_seed(7)
+    C = 1024
+    # --- ConvT: z[n,218] -> [n,1024,4,4]
+    z = _bf(torch.randn(n, 218, device=cuda))
+    w = _bf(torch.randn(218, C, 4, 4, device=cuda) * 0.05)
+    b = torch.randn(C, device=cuda)
+    ref = TF.conv_transpose2d(z.view(n, 218, 1, 1), w, b, stride=1, padding=0)
+    a = tc.pad_rows(z, 256)
+    out = tc.dense_scatter(a, tc.dense_pack(w, 256, False), b, C)
+    assert rel_err(tc.from_padded(out), ref) <= 1e-2
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, 5].abs().max()) == 0
+    g = _bf(torch.randn(n, C, 4, 4, device=cuda))
+    wz = torch.zeros_like(w).requires_grad_()
+    gw = torch.autograd.grad(TF.conv_transpose2d(z.view(n, 218, 1, 1), wz, None), wz, g)[0]
+    assert rel_err(tc.dense_wgrad(a, tc.to_padded(g), 218), gw) <= 2e-3
+    # --- head: y[n,1024,4,4] -> [n,19]
+    y = _bf(torch.randn(n, C, 4, 4, device=cuda))
+    wh = _bf(torch.randn(19, C, 4, 4, device=cuda) * 0.02)
+    bh = torch.randn(19, device=cuda)
+    yp = tc.to_padded(y)
+    refh = TF.conv2d(y, wh, bh).view(n, 19)
+    outh = tc.dense_gather(yp, tc.dense_pack(wh, 32, True), bh, 19)
+    assert rel_err(outh, refh) <= 2e-3
+    gh = _bf(torch.randn(n, 19, device=cuda))
+    whz = torch.zeros_like(wh).requires_grad_()
+    yr = y.clone().requires_grad_()
+    gwh = torch.autograd.grad(TF.conv2d(y, whz, None).view(n, 19), whz, gh)[0]
+    gy = torch.autograd.grad(TF.conv2d(yr, wh, None).view(n, 19), yr, gh)[0]
+    ah = tc.pad_rows(gh, 64)
+    assert rel_err(tc.dense_wgrad(ah, yp, 19), gwh) <= 2e-3
+    dxp = tc.dense_scatter(ah, tc.dense_pack(wh, 64, False), None, C, mask=yp, mask_act=ACT_LRELU, slope=0.1)
+    assert rel_err(tc.from_padded(dxp), gy * torch.where(y > 0, 1.0, 0.1)) <= 1e-2
