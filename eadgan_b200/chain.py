@@ -265,8 +265,11 @@ class _ChainFn(torch.autograd.Function):
             rec["inp"] = inp
             if st.bn is not None:
                 bn = st.bn
-                count = float(out_shape[0] * out_shape[2] * out_shape[3])
+                n_local = float(out_shape[0] * out_shape[2] * out_shape[3])
+                count = n_local
+                sum_x = stats                      # this rank's S(x) (first C entries), kept for backward
                 if Fn._allreduce_sum is not None:
+                    sum_x = stats[:cout].clone()
                     Fn._allreduce_sum(stats)
                     count *= Fn._world_size
                 mean = torch.empty(cout, device=dev, dtype=torch.float32)
@@ -277,7 +280,8 @@ class _ChainFn(torch.autograd.Function):
                 xd, yd = t4(out.view()), t4(y.view())
                 call("eadgan_bn_apply", C.byref(xd), out_shape[0], cout, out_shape[2], out_shape[3], ptr(mean),
                      ptr(invstd), ptr(gamma), ptr(beta), st.act[0], float(st.act[1]), C.byref(yd), st_)
-                rec.update(pre=out, mean=mean, invstd=invstd, gamma=gamma, beta=beta, count=count)
+                rec.update(pre=out, mean=mean, invstd=invstd, gamma=gamma, beta=beta, count=count, n_local=n_local,
+                           sum_x=sum_x)
                 out = y
             rec["y"] = out
             saved.append(rec)
@@ -316,7 +320,13 @@ class _ChainFn(torch.autograd.Function):
                 call("eadgan_bn_bwd_apply", C.byref(gd), C.byref(xd), C.byref(yd), n, cout, oh, ow, ptr(sv["mean"]),
                      ptr(sv["invstd"]), ptr(sv["gamma"]), ptr(sv["beta"]), st.act[0], float(st.act[1]), ptr(sums),
                      float(sv["count"]), C.byref(gd), st_)  # in place: dz overwrites g
-                dbeta, dgamma = local[:cout].float(), local[cout:].float()
+                # dgamma / dbeta, and the conv-bias gradient (= sum of dx, zero up to rounding) in closed
+                # form from the fp64 sums: no extra pass over dz
+                small = torch.empty(3 * cout, device=dev, dtype=torch.float32)
+                dgamma, dbeta, db_bn = small[:cout], small[cout:2 * cout], small[2 * cout:]
+                call("eadgan_bn_bwd_finalize", ptr(local), ptr(sums), ptr(sv["sum_x"]), float(sv["n_local"]),
+                     float(sv["count"]), ptr(sv["mean"]), ptr(sv["invstd"]), ptr(sv["gamma"]), cout, ptr(dgamma),
+                     ptr(dbeta), ptr(db_bn) if sv["has_b"] else None, st_)
                 dz = g
             elif st.act[0] != ACT_NONE and not g_masked:
                 if g.fmt != "ext" or sv["y"].fmt != "ext":
@@ -324,7 +334,10 @@ class _ChainFn(torch.autograd.Function):
                 dz = _Buf(Fn.act_bwd(g.t, sv["y"].t, st.act[0], st.act[1]), "ext")
             else:
                 dz = g
-            db = _chan_sums(dz, cout) if sv["has_b"] else None
+            if st.bn is not None:
+                db = db_bn if sv["has_b"] else None
+            else:
+                db = _chan_sums(dz, cout) if sv["has_b"] else None
             prev = stages[si - 1] if si > 0 else None
             need_dx = si > 0 or ctx.needs_input_grad[0]
             fuse = need_dx and prev is not None and prev.bn is None and prev.act[0] != ACT_NONE

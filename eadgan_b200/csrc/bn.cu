@@ -219,6 +219,26 @@ __global__ void bn_finalize_kernel(const double* sums, double count, int c, floa
   }
 }
 
+
+// dgamma / dbeta (local sums) and the gradient of a conv bias feeding this BatchNorm, all from the
+// fp64 partial sums -- no extra pass over the activation.  sum(dx) over the local elements is
+//   gamma*invstd*(S_dz_loc - n_loc*S_dz/count - S_xhat_loc*S_dzxhat/count),  S_xhat_loc = (S_x_loc - n_loc*mean)*invstd
+// (mathematically zero on one rank: torch's own value there is fp32 summation noise).
+__global__ void bn_bwd_finalize_kernel(const double* loc, const double* glob, const double* fwd_loc, double n_loc,
+                                       double count, const float* mean, const float* invstd, const float* gamma,
+                                       int c, float* dgamma, float* dbeta, float* dbias) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  if (dbeta) dbeta[ch] = (float)loc[ch];
+  if (dgamma) dgamma[ch] = (float)loc[c + ch];
+  if (dbias) {
+    const double is = (double)invstd[ch];
+    const double sxhat = fwd_loc ? (fwd_loc[ch] - n_loc * (double)mean[ch]) * is : 0.0;
+    const double ga = gamma ? (double)gamma[ch] : 1.0;
+    dbias[ch] = (float)(ga * is * (loc[ch] - n_loc * glob[ch] / count - sxhat * glob[c + ch] / count));
+  }
+}
+
 int make_geo(Geo* g, int n, int c, int h, int w, const eadgan_tensor4* const* ts, int nt,
              const char* who) {
   EG_REQUIRE(n > 0 && c > 0 && h > 0 && w > 0, EADGAN_ERR_INVALID, "%s: bad extents", who);
@@ -338,5 +358,17 @@ extern "C" int eadgan_bn_bwd_apply(const eadgan_tensor4* dy, const eadgan_tensor
   a.sums = sums; a.count = count;
   bn_bwd_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
   EG_LAUNCH_CHECK("bn_bwd_apply_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_bn_bwd_finalize(const double* local_sums, const double* global_sums,
+                                      const double* fwd_local_sum_x, double n_local, double count,
+                                      const float* mean, const float* invstd, const float* gamma, int c,
+                                      float* dgamma, float* dbeta, float* dbias, void* stream) {
+  EG_REQUIRE(local_sums && global_sums && mean && invstd && c > 0 && count > 0 && n_local > 0, EADGAN_ERR_INVALID,
+             "bn_bwd_finalize: bad arguments");
+  bn_bwd_finalize_kernel<<<(c + 127) / 128, 128, 0, (cudaStream_t)stream>>>(
+      local_sums, global_sums, fwd_local_sum_x, n_local, count, mean, invstd, gamma, c, dgamma, dbeta, dbias);
+  EG_LAUNCH_CHECK("bn_bwd_finalize_kernel");
   return 0;
 }

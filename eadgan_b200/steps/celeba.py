@@ -85,8 +85,9 @@ class CelebAStep:
         if rec is not None:
             rec[-1]["params_after"] = [p.detach().clone() for g in opt.param_groups for p in g["params"]]
 
-    def __call__(self, imgs, z, code, labels, record=None):
-        """imgs [B,3,64,64] in [-1,1]; z [B,200]; code [B,8]; labels [B] int64 -- all on the device."""
+    def __call__(self, imgs, z, code, labels, record=None, after_phase=None):
+        """imgs [B,3,64,64] in [-1,1]; z [B,200]; code [B,8]; labels [B] int64 -- all on the device.
+        ``after_phase(i)`` (tests only) runs after the optimiser step of phase i = 0, 1."""
         G, D = self.G, self.D
         B = imgs.shape[0]
         valid = torch.ones(B, device=imgs.device)
@@ -104,6 +105,8 @@ class CelebAStep:
         self._snap(self.opt_G, record, "G")
         self.opt_G.step()
         self._after(self.opt_G, record)
+        if after_phase is not None:
+            after_phase(0)
 
         # phase D -- :353-366
         self.opt_D.zero_grad()
@@ -114,6 +117,8 @@ class CelebAStep:
         self._snap(self.opt_D, record, "D")
         self.opt_D.step()
         self._after(self.opt_D, record)
+        if after_phase is not None:
+            after_phase(1)
 
         # phase info -- :375-401
         self.opt_info.zero_grad()

@@ -201,6 +201,13 @@ int eadgan_bn_bwd_apply(const eadgan_tensor4* dy, const eadgan_tensor4* x, const
                         int n, int c, int h, int w, const float* mean, const float* invstd,
                         const float* gamma, const float* beta, int act, float slope,
                         const double* sums, double count, const eadgan_tensor4* dx, void* stream);
+/* dgamma = local S(dz*xhat), dbeta = local S(dz) as fp32, and (dbias != NULL) the gradient of a conv
+ * bias feeding this BatchNorm = sum over the local elements of dx, in closed form from the sums
+ * (fwd_local_sum_x = this rank's S(x) of the forward; n_local = local n*h*w; count = global). */
+int eadgan_bn_bwd_finalize(const double* local_sums, const double* global_sums,
+                           const double* fwd_local_sum_x, double n_local, double count,
+                           const float* mean, const float* invstd, const float* gamma, int c,
+                           float* dgamma, float* dbeta, float* dbias, void* stream);
 /* eval mode: y = act(gamma*(x-running_mean)/sqrt(running_var+eps)+beta) */
 int eadgan_bn_eval(const eadgan_tensor4* x, int n, int c, int h, int w, const float* running_mean,
                    const float* running_var, float eps, const float* gamma, const float* beta,

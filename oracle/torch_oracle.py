@@ -174,6 +174,13 @@ def _params(opt):
     return [p.detach().clone() for g in opt.param_groups for p in g["params"]]
 
 
+def _state(G, D):
+    """full module state (weights, BN running stats, spectral-norm u/v) after a phase: lets a test restart
+    the next phase of another implementation from THIS run's state (SURVEY.md section 7.3-1 iv)."""
+    return {"G": {k: v.detach().clone() for k, v in G.state_dict().items()},
+            "D": {k: v.detach().clone() for k, v in D.state_dict().items()}}
+
+
 def step_celeba(st, imgs, draws, record=True):
     """One iteration of celebA/EAD-GAN_celebA.py:297-401 on batch ``imgs`` [B,3,64,64]."""
     G, D = st["G"], st["D"]
@@ -202,6 +209,7 @@ def step_celeba(st, imgs, draws, record=True):
     st["opt_G"].step()
     if record:
         rec["phases"][-1]["params_after"] = _params(st["opt_G"])
+        rec["phases"][-1]["state_after"] = _state(G, D)
 
     # ---- phase D  (:353-366)
     st["opt_D"].zero_grad()
@@ -216,6 +224,7 @@ def step_celeba(st, imgs, draws, record=True):
     st["opt_D"].step()
     if record:
         rec["phases"][-1]["params_after"] = _params(st["opt_D"])
+        rec["phases"][-1]["state_after"] = _state(G, D)
 
     # ---- phase info  (:375-401)
     st["opt_info"].zero_grad()

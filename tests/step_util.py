@@ -1,0 +1,78 @@
+"""Shared helper of the step-level GPU tests and tools/diag_step.py: run the oracle and OUR CelebA step on
+the same seeded inputs and weights, restarting every phase of ours from the ORACLE's post-phase state so
+that Adam's sign(g) noise of one phase does not contaminate the next (SURVEY.md section 7.3-1 iv)."""
+import os
+
+import numpy as np
+import torch
+
+
+def tensor_err(a, b, floor=0.0):
+    """tensor-normalised max error max|a-b| / max(max|b|, floor)."""
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return (a - b).abs().max().item() / max(b.abs().max().item(), floor, 1e-300)
+
+
+def l2_err(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a - b).norm() / (b.norm() + 1e-300))
+
+
+def cosine(a, b):
+    a, b = a.detach().double().cpu().flatten(), b.detach().double().cpu().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-300))
+
+
+def run_pair(dev, B, precision, oracle_dtype=torch.float64, seed=0, sync=True):
+    """-> (oracle record, our per-phase record, our losses, oracle state, our step object)."""
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = precision
+    imgs = O.synth_celeba_images(B, seed).to(dev)
+    draws = O.sample_celeba(np.random.RandomState(seed), B)
+    st = O.build_celeba(seed=seed, device=dev, dtype=oracle_dtype)
+    ref = O.step_celeba(st, imgs.to(oracle_dtype), draws)
+    ours = CelebAStep(seed=seed, device=dev)
+
+    def after_phase(i):
+        if not sync:
+            return
+        snap = ref["phases"][i]["state_after"]
+        ours.G.load_state_dict({k: v.to(torch.float32) if v.is_floating_point() else v for k, v in snap["G"].items()})
+        ours.D.load_state_dict({k: v.to(torch.float32) if v.is_floating_point() else v for k, v in snap["D"].items()})
+
+    rec = []
+    losses = ours(imgs, draws["z"].to(dev), draws["code"].to(dev), draws["labels"].to(dev), record=rec,
+                  after_phase=after_phase)
+    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
+
+
+def grad_names(step):
+    g = [n for n, _ in step.G.named_parameters()]
+    d = [n for n, _ in step.D.named_parameters()]
+    return [["G." + n for n in g], ["D." + n for n in d], ["G." + n for n in g] + ["D." + n for n in d]]
+
+
+# conv biases directly in front of a train-mode BatchNorm: their gradient is mathematically zero (the
+# reference's own value is fp32 summation noise), so they are normalised by the sibling weight gradient
+ZERO_GRAD = {"G.conv_blocks.1.bias": "G.conv_blocks.1.weight", "G.conv_blocks.4.bias": "G.conv_blocks.4.weight",
+             "G.conv_blocks.7.bias": "G.conv_blocks.7.weight"}
+
+
+def phase_errors(names, ours_grads, ref_grads):
+    """-> {name: (max_err, l2_err, cosine)}.  Zero-gradient tensors use their sibling weight's scale
+    (l2 / cosine = None); so do tensors with fewer than 16 elements (the [3] bias of G's last layer is
+    a sum of 4096*B random-sign terms: ill-conditioned as a 3-vector, well-defined as one more column
+    of the layer's [dW | db] gradient)."""
+    refs = dict(zip(names, ref_grads))
+    out = {}
+    for n, a, b in zip(names, ours_grads, ref_grads):
+        sib = ZERO_GRAD.get(n)
+        if sib is None and b.numel() < 16 and n.endswith(".bias"):
+            sib = n[:-5] + ".weight"
+        if sib is not None:
+            floor = refs[sib].abs().max().item()
+            out[n] = (tensor_err(a, b, floor), None, None)
+        else:
+            out[n] = (tensor_err(a, b), l2_err(a, b), cosine(a, b))
+    return out

@@ -1,64 +1,64 @@
-"""-m gpu: one full CelebA training step (three phases, three Adams) through the drop-in
-modules vs the oracle restatement (stock torch fp32, TF32 off) on identical seeded inputs
-and identical seeded random-init weights.  Protocol of SURVEY.md section 7.3-1: tensor-
-normalised max error per gradient tensor; Adam sign noise means post-step weights are
-compared through the update magnitude, not bit-wise."""
-import numpy as np
+"""-m gpu: one full CelebA training step (three phases, three Adams; celebA/EAD-GAN_celebA.py:296-401)
+through the drop-in modules vs the oracle restatement on identical seeded inputs and identical seeded
+random-init weights.
+
+Protocol: the torch fp64 oracle is the referee; every phase of OUR run starts
+from the oracle's post-phase state (tests/step_util.py), so Adam's lr*sign(g) noise does not cascade;
+gradients are compared per tensor with the tensor-normalised max error max|a-b|/max|b| (conv biases in
+front of a train-mode BatchNorm -- mathematically zero gradient -- use their weight's scale); Adam is
+tested in isolation on identical gradients in tests/test_ops_gpu.py.
+"""
 import pytest
 import torch
 
+import step_util as U
 from conftest import rel_err
 
 pytestmark = pytest.mark.gpu
 
 
-def _run_pair(cuda, B, precision):
-    import os
-    os.environ["EADGAN_PRECISION"] = precision
-    from eadgan_b200.steps.celeba import CelebAStep
-    from oracle import torch_oracle as O
-    imgs = O.synth_celeba_images(B, 0)
-    draws = O.sample_celeba(np.random.RandomState(0), B)
-    torch.set_num_threads(os.cpu_count() or 1)
-    st = O.build_celeba(seed=0, device="cpu")   # the oracle on the host CPU (oneDNN fp32)
-    ref = O.step_celeba(st, imgs, draws)
-    ours = CelebAStep(seed=0, device=cuda)
-    rec = []
-    losses = ours(imgs.to(cuda), draws["z"].to(cuda), draws["code"].to(cuda), draws["labels"].to(cuda), record=rec)
-    rec = [{k: ([None if t is None else t.cpu() for t in v] if isinstance(v, list) else v) for k, v in ph.items()} for ph in rec]
-    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
-
-
 def test_celeba_step_fp32(cuda):
-    ref, rec, losses, st, ours = _run_pair(cuda, 8, "fp32")
+    ref, rec, losses, st, ours = U.run_pair(cuda, 8, "fp32")
     for k in ("g_loss", "d_loss", "info_loss"):
         assert abs(losses[k] - ref["losses"][k]) <= 2e-5 * max(1.0, abs(ref["losses"][k])), (k, losses, ref["losses"])
-    # phase G starts from identical weights.  A single ReLU/LeakyReLU gate flip (a pre-activation
-    # within fp32 rounding of 0) moves every upstream gradient by 4e-4..1.4e-3 in the reference
-    # run against ITSELF in fp64, so 3e-3 is the step-level bound; the
-    # 1e-5 bound is carried by the per-operator tests on identical inputs.
-    # (tensors whose reference gradient is mathematically zero -- conv biases feeding a train-mode
-    # BatchNorm, ~1e-9 of fp32 noise -- are compared on an absolute floor instead)
-    errs = [rel_err(go, gr) if float(gr.abs().max()) > 1e-6 else float((go - gr).abs().max())
-            for go, gr in zip(rec[0]["grads"], ref["phases"][0]["grads"])]
-    assert max(errs) <= 1e-2, errs
-    assert sorted(errs)[len(errs) // 2] <= 5e-3, errs
-    # later phases start from Adam-updated weights (lr * sign(g) noise): looser bound
-    for ph in (1, 2):
-        errs = [rel_err(go, gr) if float(gr.abs().max()) > 1e-6 else float((go - gr).abs().max())
-                for go, gr in zip(rec[ph]["grads"], ref["phases"][ph]["grads"])]
-        assert max(errs) <= 5e-2, (ph, errs)
+    # A single ReLU/LeakyReLU gate flip (a pre-activation within fp32 rounding of 0) moves every upstream
+    # gradient by 4e-4..1.4e-3 in the reference run against ITSELF in fp64, so the
+    # step-level bound is 1e-2 max / 5e-3 median; the 1e-5 bound is carried by the per-operator tests.
+    names = U.grad_names(ours)
+    for ph in range(3):
+        errs = U.phase_errors(names[ph], rec[ph]["grads"], ref["phases"][ph]["grads"])
+        mx = sorted(v[0] for v in errs.values())
+        assert mx[-1] <= 1e-2, (ph, errs)
+        assert mx[len(mx) // 2] <= 5e-3, (ph, errs)
     # BN running statistics and spectral-norm vectors after the whole step
-    so, sr = {k: v.cpu() for k, v in ours.G.state_dict().items()}, st["G"].state_dict()
+    so, sr = ours.G.state_dict(), st["G"].state_dict()
     for k in sr:
         if "running" in k:
             assert rel_err(so[k], sr[k]) <= 1e-4, k
         if "num_batches" in k:
             assert int(so[k]) == int(sr[k]) == 2
-    so, sr = {k: v.cpu() for k, v in ours.D.state_dict().items()}, st["D"].state_dict()
+    so, sr = ours.D.state_dict(), st["D"].state_dict()
     for k in sr:
         if k.endswith("_u") or k.endswith("_v"):
             assert rel_err(so[k], sr[k]) <= 1e-3, k
+
+
+def test_celeba_step_fp32_post_step_weights(cuda):
+    """post-step weights against torch fp32 + torch.optim.Adam.  Adam's first step is lr*g/(|g|+1e-8): where
+    the gradient is well above eps and above the two runs' own disagreement, the updated weights must agree
+    to 2e-3 of one step; nowhere may they differ by more than the full step size."""
+    ref, rec, losses, st, ours = U.run_pair(cuda, 8, "fp32", oracle_dtype=torch.float32)
+    checked = 0
+    for ph, lr in ((0, 1e-3), (1, 2e-4), (2, 2e-4)):
+        for a, b, go, gr in zip(rec[ph]["params_after"], ref["phases"][ph]["params_after"], rec[ph]["grads"],
+                                ref["phases"][ph]["grads"]):
+            d = (a.double() - b.double()).abs()
+            assert float(d.max()) <= 2.001 * lr
+            ok = (gr.abs() > 1e-5) & (gr.abs() > 100 * (go - gr).abs())
+            if bool(ok.any()):
+                checked += int(ok.sum())
+                assert float(d[ok].max()) <= 2e-3 * lr + 1e-7 * float(b.abs().max()), float(d[ok].max())
+    assert checked > 1_000_000
 
 
 def test_celeba_state_dict_roundtrip(cuda):
@@ -71,16 +71,29 @@ def test_celeba_state_dict_roundtrip(cuda):
     ours.G.load_state_dict(st["G"].state_dict())
     ours.D.load_state_dict(st["D"].state_dict())
     assert list(ours.D.state_dict().keys()) == list(st["D"].state_dict().keys())
+    assert list(ours.G.state_dict().keys()) == list(st["G"].state_dict().keys())
 
 
-def test_celeba_step_bf16(cuda):
-    """bf16 tcgen05 chain: north_star tolerance 2e-2 (max relative error, tensor-normalised)."""
-    ref, rec, losses, st, ours = _run_pair(cuda, 16, "bf16")
+@pytest.mark.parametrize("B", [16, 64])
+def test_celeba_step_bf16(cuda, B):
+    """bf16 tcgen05 chain.  Losses: north_star tolerance 2e-2.  Gradients: any two bf16 evaluations of these
+    nets flip ~0.1-0.3 % of the LeakyReLU(0.1)/ReLU gates against fp32 (a pre-activation within bf16 rounding
+    of 0), which is a ~5-10 % L2 perturbation of every upstream gradient whatever the kernel -- so the
+    whole-step check is direction (cosine) and L2; the 2e-2 max bound is carried per layer on identical
+    inputs by tests/test_tc_gpu.py and on gate-insensitive stacks by tests/test_chain_gpu.py."""
+    ref, rec, losses, st, ours = U.run_pair(cuda, B, "bf16")
     for k in ("g_loss", "d_loss", "info_loss"):
         assert abs(losses[k] - ref["losses"][k]) <= 2e-2 * max(1.0, abs(ref["losses"][k])), (k, losses, ref["losses"])
-    # gradients: bf16 gate flips (tests/test_chain_gpu.py docstring) -> direction / L2 metrics
-    for go, gr in zip(rec[0]["grads"], ref["phases"][0]["grads"]):
-        if float(gr.abs().max()) <= 1e-6:
-            continue
-        a, b = go.double().flatten().cpu(), gr.double().flatten()
-        assert float((a @ b) / (a.norm() * b.norm())) >= 0.97
+    names = U.grad_names(ours)
+    for ph in range(3):
+        errs = U.phase_errors(names[ph], rec[ph]["grads"], ref["phases"][ph]["grads"])
+        for n, (mx, l2, cs) in errs.items():
+            if cs is None:
+                assert mx <= 2e-2, (ph, n, mx)      # zero-gradient biases: closed form, exact
+            else:
+                assert cs >= 0.95, (ph, n, cs)
+                assert l2 <= 0.35, (ph, n, l2)
+    so, sr = ours.G.state_dict(), st["G"].state_dict()
+    for k in sr:
+        if "running" in k:
+            assert rel_err(so[k], sr[k]) <= 2e-2, k

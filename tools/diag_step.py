@@ -1,42 +1,42 @@
-"""GPU diagnostic: phase-G gradients of the CelebA step -- ours (fp32 / bf16) and the torch fp32
-oracle, each against the torch fp64 oracle (SURVEY.md section 7.3-1 referee protocol)."""
+"""GPU diagnostic: per-phase gradients of the CelebA step -- ours (fp32 / bf16) and the torch fp32 oracle,
+each against the torch fp64 oracle, phases restarted from the oracle's state (tests/step_util.py)."""
 import os
 import sys
 
-import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
-from eadgan_b200.steps.celeba import CelebAStep  # noqa: E402
+import step_util as U  # noqa: E402
 from oracle import torch_oracle as O  # noqa: E402
+import numpy as np  # noqa: E402
 
 dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
+seed = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+precs = sys.argv[3].split(",") if len(sys.argv) > 3 else ["fp32", "bf16"]
 
-
-def rel(a, b):
-    a, b = a.detach().double(), b.detach().double()
-    d = b.abs().max().item()
-    return (a - b).abs().max().item() / d if d > 1e-6 else (a - b).abs().max().item()
-
-
-imgs = O.synth_celeba_images(B, 0).to(dev)
-draws = O.sample_celeba(np.random.RandomState(0), B)
-r64 = O.step_celeba(O.build_celeba(0, device=dev, dtype=torch.float64), imgs.double(), draws)
-r32 = O.step_celeba(O.build_celeba(0, device=dev), imgs, draws)
-print("losses fp64", r64["losses"])
-print("losses ref32", r32["losses"])
-for prec in ("fp32", "bf16"):
-    os.environ["EADGAN_PRECISION"] = prec
-    rec = []
-    out = CelebAStep(seed=0, device=dev)(imgs, draws["z"].to(dev), draws["code"].to(dev), draws["labels"].to(dev), record=rec)
-    print(f"losses ours {prec}", {k: float(v) for k, v in out.items()})
+imgs = O.synth_celeba_images(B, seed).to(dev)
+draws = O.sample_celeba(np.random.RandomState(seed), B)
+r32 = O.step_celeba(O.build_celeba(seed, device=dev), imgs, draws)
+for prec in precs:
+    ref, rec, losses, st, ours = U.run_pair(dev, B, prec, seed=seed)
+    names = U.grad_names(ours)
+    print(f"B={B} seed={seed} losses fp64 {ref['losses']}\n   ref32 {r32['losses']}\n   ours-{prec} {losses}")
     for ph in range(3):
-        eo = [rel(a, b) for a, b in zip(rec[ph]["grads"], r64["phases"][ph]["grads"])]
-        er = [rel(a, b) for a, b in zip(r32["phases"][ph]["grads"], r64["phases"][ph]["grads"])]
-        print(f"  phase {ph} ours-{prec} vs fp64: max {max(eo):.2e} median {sorted(eo)[len(eo)//2]:.2e} | ref32 vs fp64: max {max(er):.2e} median {sorted(er)[len(er)//2]:.2e}")
-        if ph == 0:
-            print("    ours:", " ".join(f"{e:.1e}" for e in eo))
-            print("    ref :", " ".join(f"{e:.1e}" for e in er))
+        eo = U.phase_errors(names[ph], rec[ph]["grads"], ref["phases"][ph]["grads"])
+        er = U.phase_errors(names[ph], r32["phases"][ph]["grads"], ref["phases"][ph]["grads"]) if ph == 0 else None
+        mx = [v[0] for v in eo.values()]
+        l2 = [v[1] for v in eo.values() if v[1] is not None]
+        cs = [v[2] for v in eo.values() if v[2] is not None]
+        print(f"  phase {ph} ours-{prec} vs fp64: max-err max {max(mx):.2e} median {sorted(mx)[len(mx)//2]:.2e} | "
+              f"L2 max {max(l2):.2e} median {sorted(l2)[len(l2)//2]:.2e} | cos min {min(cs):.5f}")
+        if er is not None:
+            mr = [v[0] for v in er.values()]
+            print(f"          ref32 vs fp64: max-err max {max(mr):.2e} median {sorted(mr)[len(mr)//2]:.2e}")
+        if "-v" in sys.argv:
+            for (n, v), gr in zip(eo.items(), ref["phases"][ph]["grads"]):
+                print(f"      {n:32s} |g|max {gr.abs().max().item():.2e} max {v[0]:.2e}" + ("" if v[1] is None else f" l2 {v[1]:.2e} cos {v[2]:.5f}"))
