@@ -58,7 +58,7 @@ _PROTOS = {
     "eadgan_tc_pack_w_dgrad": [_P, _P, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_pack": [_P, _I, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_gather": [_P, _P, _P, _P, _I, _I, _I, _P],
-    "eadgan_tc_dense_scatter": [_P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _P],
+    "eadgan_tc_dense_scatter": [_P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_wgrad": [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P],
     "eadgan_tc_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
     "eadgan_tc_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
@@ -90,6 +90,8 @@ _PROTOS = {
     "eadgan_mi_bwd": [_P, _P, _P, _I, _I, _P, _P],
     "eadgan_adam_step": [C.POINTER(AdamTensors), _D, _D, _D, _D, _D, _F, _P],
     "eadgan_fill_f32": [_P, _L, _F, _P],
+    "eadgan_f64_to_f32": [_P, _P, _L, _P],
+    "eadgan_zero_halo": [_P, _I, _I, _I, _I, _P],
 }
 _SPECIAL = {
     "eadgan_last_error": ([], C.c_char_p),

@@ -300,6 +300,7 @@ class _ChainFn(torch.autograd.Function):
         dev = gout.device
         g = _Buf(gout.contiguous(), "ext")
         g_masked = False
+        db_sums = None   # fp64 per-channel sums of g, accumulated by the epilogue of the kernel that produced g
         grads = []
         for si in range(len(stages) - 1, -1, -1):
             st, sv = stages[si], saved[si]
@@ -334,16 +335,29 @@ class _ChainFn(torch.autograd.Function):
                 dz = _Buf(Fn.act_bwd(g.t, sv["y"].t, st.act[0], st.act[1]), "ext")
             else:
                 dz = g
-            if st.bn is not None:
-                db = db_bn if sv["has_b"] else None
+            if not sv["has_b"]:
+                db = None
+            elif st.bn is not None:
+                db = db_bn
+            elif db_sums is not None and dz is g:
+                db = torch.empty(cout, device=dev, dtype=torch.float32)
+                call("eadgan_f64_to_f32", ptr(db_sums), ptr(db), cout, st_)
             else:
-                db = _chan_sums(dz, cout) if sv["has_b"] else None
+                db = _chan_sums(dz, cout)
+            db_sums = None
             prev = stages[si - 1] if si > 0 else None
             need_dx = si > 0 or ctx.needs_input_grad[0]
             fuse = need_dx and prev is not None and prev.bn is None and prev.act[0] != ACT_NONE
             mask_act, mask_slope = (prev.act if fuse else (ACT_NONE, 0.0))
             in_shape = (d.n, d.c, d.h, d.w) if st.kind == "conv" else (d.n, d.k, d.p, d.q)
             dx = None
+            # the dx computed here IS the previous stage's pre-activation gradient when that stage has no BN and
+            # its activation backward is fused (or absent): let the producing epilogue also sum it per channel
+            # (= that stage's bias gradient), instead of a separate pass over dx
+            want_sums = (need_dx and prev is not None and prev.bn is None and saved[si - 1]["has_b"]
+                         and (fuse or prev.act[0] == ACT_NONE) and in_shape[1] <= 1024)
+            sums_buf = torch.zeros(in_shape[1], device=dev, dtype=torch.float64) if want_sums else None
+            sums_used = False
             # ---- 2./3. weight gradient and input gradient -----------------------------------------
             if impl == "dense_T":
                 dw = tc.dense_wgrad(sv["a"], dz.padded(), d.k)
@@ -353,7 +367,8 @@ class _ChainFn(torch.autograd.Function):
                 if need_dx and (si > 0) and (not fuse or sv["inp"].fmt == "pad"):
                     dx = _Buf(tc.dense_scatter(a, tc.dense_pack(sv["w"], 64, False), None, d.c,
                                                mask=sv["inp"].t if fuse else None, mask_act=mask_act,
-                                               slope=mask_slope), "pad")
+                                               slope=mask_slope, chan_sums=sums_buf), "pad")
+                    sums_used = want_sums
             else:
                 ca = _calloc(d) if impl == "tc" else d.c
                 x_big, dy_small = (sv["inp"], dz) if st.kind == "conv" else (dz, sv["inp"])
@@ -377,12 +392,14 @@ class _ChainFn(torch.autograd.Function):
                         if st.kind == "conv":
                             dx_t = tc.dgrad(dz.padded(), wpk, None, ca, mask=sv["inp"].t if fuse else None,
                                             mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0),
-                                            c_real=d.c if ca != d.c else 0)
+                                            c_real=d.c if ca != d.c else 0, stats=sums_buf, stats_mode=2)
                         else:
                             dzp = dz.t if dz.fmt == "pad" else tc.to_padded(dz.t, ca)
                             dx_t = tc.fprop(dzp, wpk, None, in_shape[1], mask=sv["inp"].t if fuse else None,
-                                            mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0))
+                                            mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0),
+                                            stats=sums_buf, stats_mode=2)
                         dx = _Buf(dx_t, "ext" if si == 0 else "pad")
+                        sums_used = want_sums
             if need_dx and dx is None:   # generic SIMT input gradient on the same buffers
                 if si > 0:
                     dx = _Buf(tc.alloc_padded(in_shape[0], in_shape[2], in_shape[3], in_shape[1], dev), "pad")
@@ -398,6 +415,7 @@ class _ChainFn(torch.autograd.Function):
                      float(mask_slope), st_)
             if need_dx:
                 g, g_masked = dx, fuse
+                db_sums = sums_buf if sums_used else None
             stage_grads = [dw, db]
             if st.bn is not None:
                 stage_grads += [dgamma, dbeta]

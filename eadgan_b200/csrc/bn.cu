@@ -203,6 +203,191 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(BwdArgs a, Geo g) {
   });
 }
 
+
+// ---------------- NHWC bf16 fast paths (the private halo-padded buffers of the chain executor) --------
+// A row (n, y) of the interior is one contiguous run of w*c bf16 = w*c/8 16-byte vectors.  256 threads per
+// block, grid-stride over rows; vector v of a row holds channels 8*(v % (c/8)).., and because c/8 divides
+// 256 every thread keeps ONE channel group for the whole kernel, so the per-channel parameters live in
+// registers.  Bytes per element: apply 2R+2W, bwd_reduce 4R (dy, x; the ReLU/LeakyReLU gate is recomputed
+// from x with the forward's own expression instead of reading y), bwd_apply 4R+2W.
+struct Nhwc8 {
+  int n, c, h, w;
+  int cv;         // c / 8
+  int row_vecs;   // w * c / 8
+};
+
+__device__ __forceinline__ void bf8_to_f32(const uint4 u, float* f) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    f[2 * e] = __uint_as_float(w[e] << 16);
+    f[2 * e + 1] = __uint_as_float(w[e] & 0xffff0000u);
+  }
+}
+__device__ __forceinline__ uint4 f32_to_bf8(const float* f) {
+  uint32_t w[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+    w[e] = *reinterpret_cast<uint32_t*>(&h2);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ const uint4* row_ptr(const eadgan_tensor4& t, int b, int y) {
+  return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.ptr) + (int64_t)b * t.sn + (int64_t)y * t.sh);
+}
+
+struct ChanParams { float mean[8], is[8], ga[8], be[8]; };
+__device__ __forceinline__ void load_params(ChanParams& p, int ch0, const float* mean, const float* invstd,
+                                            const float* gamma, const float* beta) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p.mean[j] = mean[ch0 + j];
+    p.is[j] = invstd[ch0 + j];
+    p.ga[j] = gamma ? gamma[ch0 + j] : 1.f;
+    p.be[j] = beta ? beta[ch0 + j] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_apply_nhwc8_kernel(ApplyArgs a, Nhwc8 g) {
+  ChanParams p;
+  const int ch0 = (threadIdx.x % g.cv) * 8;
+  load_params(p, ch0, a.mean, a.invstd, a.gamma, a.beta);
+  if (a.eval) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) p.is[j] = rsqrtf(p.is[j] + a.eps);
+  }
+  const int rows = g.n * g.h;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / g.h, y = row - b * g.h;
+    const uint4* xr = row_ptr(a.x, b, y);
+    uint4* yr = const_cast<uint4*>(row_ptr(a.y, b, y));
+    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
+      float f[8];
+      bf8_to_f32(__ldg(xr + v), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = eg_act((f[j] - p.mean[j]) * p.is[j] * p.ga[j] + p.be[j], a.act, a.slope);
+      yr[v] = f32_to_bf8(f);
+    }
+  }
+}
+
+// gate of a ReLU / LeakyReLU that follows the affine transform, recomputed from x exactly as apply did
+__device__ __forceinline__ float bn_gate(float x, const ChanParams& p, int j, float slope_neg) {
+  const float v = (x - p.mean[j]) * p.is[j] * p.ga[j] + p.be[j];
+  return v > 0.f ? 1.f : slope_neg;
+}
+
+template <bool GATE_FROM_X>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc8_kernel(BwdArgs a, Nhwc8 g, double* sums) {
+  __shared__ double sh[2 * 1024];
+  for (int i = threadIdx.x; i < 2 * g.c; i += 256) sh[i] = 0.0;
+  __syncthreads();
+  ChanParams p;
+  const int ch0 = (threadIdx.x % g.cv) * 8;
+  load_params(p, ch0, a.mean, a.invstd, a.gamma, a.beta);
+  const float slope_neg = a.act == EADGAN_ACT_RELU ? 0.f : a.slope;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  const int rows = g.n * g.h;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / g.h, y = row - b * g.h;
+    const uint4* dyr = row_ptr(a.dy, b, y);
+    const uint4* xr = row_ptr(a.x, b, y);
+    const uint4* yr = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
+    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
+      float dz[8], xv[8];
+      bf8_to_f32(__ldg(dyr + v), dz);
+      bf8_to_f32(__ldg(xr + v), xv);
+      if (GATE_FROM_X) {
+        if (a.act != EADGAN_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
+        }
+      } else {
+        float yv[8];
+        bf8_to_f32(__ldg(yr + v), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s0[j] += dz[j];
+        s1[j] += dz[j] * (xv[j] - p.mean[j]) * p.is[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[ch0 + j], (double)s0[j]);
+    atomicAdd(&sh[g.c + ch0 + j], (double)s1[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.c; i += 256) atomicAdd(&sums[i], sh[i]);
+}
+
+template <bool GATE_FROM_X>
+__global__ void __launch_bounds__(256) bn_bwd_apply_nhwc8_kernel(BwdArgs a, Nhwc8 g) {
+  ChanParams p;
+  const int ch0 = (threadIdx.x % g.cv) * 8;
+  load_params(p, ch0, a.mean, a.invstd, a.gamma, a.beta);
+  const float slope_neg = a.act == EADGAN_ACT_RELU ? 0.f : a.slope;
+  const double inv_count = 1.0 / a.count;
+  float m_dz[8], m_dzx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m_dz[j] = (float)(a.sums[ch0 + j] * inv_count);
+    m_dzx[j] = (float)(a.sums[g.c + ch0 + j] * inv_count);
+  }
+  const int rows = g.n * g.h;
+  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = row / g.h, y = row - b * g.h;
+    const uint4* dyr = row_ptr(a.dy, b, y);
+    const uint4* xr = row_ptr(a.x, b, y);
+    const uint4* yr = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
+    uint4* dxr = const_cast<uint4*>(row_ptr(a.dx, b, y));
+    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
+      float dz[8], xv[8];
+      bf8_to_f32(__ldg(dyr + v), dz);
+      bf8_to_f32(__ldg(xr + v), xv);
+      if (GATE_FROM_X) {
+        if (a.act != EADGAN_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
+        }
+      } else {
+        float yv[8];
+        bf8_to_f32(__ldg(yr + v), yv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xhat = (xv[j] - p.mean[j]) * p.is[j];
+        dz[j] = p.ga[j] * p.is[j] * (dz[j] - m_dz[j] - xhat * m_dzx[j]);
+      }
+      dxr[v] = f32_to_bf8(dz);
+    }
+  }
+}
+
+// all tensors channel-fastest bf16 rows with 16-byte aligned runs, and c/8 divides 256
+bool nhwc8_ok(const Geo& g, const eadgan_tensor4* const* ts, int nt) {
+  if (g.kind != 1 || g.c % 8 != 0 || g.c > 1024 || 256 % (g.c / 8) != 0) return false;
+  for (int i = 0; i < nt; ++i) {
+    if (!ts[i]) continue;
+    if (ts[i]->dtype != EADGAN_BF16 || (ts[i]->sn % 8) != 0 || (ts[i]->sh % 8) != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(ts[i]->ptr) & 15) != 0) return false;
+  }
+  return true;
+}
+Nhwc8 make_nhwc8(const Geo& g) { return Nhwc8{g.n, g.c, g.h, g.w, g.c / 8, g.w * g.c / 8}; }
+int nhwc8_grid(const Geo& g) {
+  const int rows = g.n * g.h, cap = 8 * eg_sm_count();
+  return rows < cap ? rows : cap;
+}
+
 __global__ void bn_finalize_kernel(const double* sums, double count, int c, float eps, float momentum,
                                    float* mean, float* invstd, float* rmean, float* rvar) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
@@ -304,6 +489,11 @@ extern "C" int eadgan_bn_apply(const eadgan_tensor4* x, int n, int c, int h, int
   EG_REQUIRE(x && y && mean && invstd, EADGAN_ERR_INVALID, "bn_apply: NULL argument");
   if (int e = make_geo(&g, n, c, h, w, ts, 2, "bn_apply")) return e;
   ApplyArgs a{*x, *y, mean, invstd, gamma, beta, act, slope, 0.f, 0};
+  if (nhwc8_ok(g, ts, 2)) {
+    bn_apply_nhwc8_kernel<<<nhwc8_grid(g), 256, 0, (cudaStream_t)stream>>>(a, make_nhwc8(g));
+    EG_LAUNCH_CHECK("bn_apply_nhwc8_kernel");
+    return 0;
+  }
   bn_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
   EG_LAUNCH_CHECK("bn_apply_kernel");
   return 0;
@@ -336,6 +526,14 @@ extern "C" int eadgan_bn_bwd_reduce(const eadgan_tensor4* dy, const eadgan_tenso
   BwdArgs a{};
   a.dy = *dy; a.x = *x; if (y) a.y = *y;
   a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
+  const bool gate_x = act == EADGAN_ACT_NONE || act == EADGAN_ACT_RELU || act == EADGAN_ACT_LRELU;
+  const eadgan_tensor4* fs[] = {dy, x, gate_x ? nullptr : y};
+  if (nhwc8_ok(g, fs, 3)) {
+    if (gate_x) bn_bwd_reduce_nhwc8_kernel<true><<<nhwc8_grid(g), 256, 0, (cudaStream_t)stream>>>(a, make_nhwc8(g), sums);
+    else bn_bwd_reduce_nhwc8_kernel<false><<<nhwc8_grid(g), 256, 0, (cudaStream_t)stream>>>(a, make_nhwc8(g), sums);
+    EG_LAUNCH_CHECK("bn_bwd_reduce_nhwc8_kernel");
+    return 0;
+  }
   bn_bwd_reduce_kernel<<<reduce_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g, sums);
   EG_LAUNCH_CHECK("bn_bwd_reduce_kernel");
   return 0;
@@ -356,6 +554,14 @@ extern "C" int eadgan_bn_bwd_apply(const eadgan_tensor4* dy, const eadgan_tensor
   a.dy = *dy; a.x = *x; if (y) a.y = *y; a.dx = *dx;
   a.mean = mean; a.invstd = invstd; a.gamma = gamma; a.beta = beta; a.act = act; a.slope = slope;
   a.sums = sums; a.count = count;
+  const bool gate_x = act == EADGAN_ACT_NONE || act == EADGAN_ACT_RELU || act == EADGAN_ACT_LRELU;
+  const eadgan_tensor4* fs[] = {dy, x, dx, gate_x ? nullptr : y};
+  if (nhwc8_ok(g, fs, 4)) {
+    if (gate_x) bn_bwd_apply_nhwc8_kernel<true><<<nhwc8_grid(g), 256, 0, (cudaStream_t)stream>>>(a, make_nhwc8(g));
+    else bn_bwd_apply_nhwc8_kernel<false><<<nhwc8_grid(g), 256, 0, (cudaStream_t)stream>>>(a, make_nhwc8(g));
+    EG_LAUNCH_CHECK("bn_bwd_apply_nhwc8_kernel");
+    return 0;
+  }
   bn_bwd_apply_kernel<<<elem_grid(g), 256, 0, (cudaStream_t)stream>>>(a, g);
   EG_LAUNCH_CHECK("bn_bwd_apply_kernel");
   return 0;

@@ -211,3 +211,43 @@ extern "C" int eadgan_fill_f32(float* p, int64_t numel, float value, void* strea
   EG_LAUNCH_CHECK("fill_kernel");
   return 0;
 }
+
+namespace {
+__global__ void f64_to_f32_kernel(const double* __restrict__ src, float* __restrict__ dst, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i] = (float)src[i];
+}
+
+// one thread per (image, halo pixel, 8-channel vector): 16-byte zero stores
+__global__ void zero_halo_kernel(uint4* __restrict__ xp, int n, int h, int w, int cv) {
+  const int per_img = 2 * (w + 2) + 2 * h;
+  const int64_t total = (int64_t)n * per_img * cv;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    const int64_t r = i / cv;
+    const int hp = (int)(r % per_img);
+    const int64_t b = r / per_img;
+    int y, x;
+    if (hp < w + 2) { y = 0; x = hp; }
+    else if (hp < 2 * (w + 2)) { y = h + 1; x = hp - (w + 2); }
+    else { const int q = hp - 2 * (w + 2); y = 1 + (q >> 1); x = (q & 1) ? w + 1 : 0; }
+    xp[((b * (h + 2) + y) * (int64_t)(w + 2) + x) * cv + v] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+}  // namespace
+
+extern "C" int eadgan_f64_to_f32(const double* src, float* dst, int64_t numel, void* stream) {
+  EG_REQUIRE(src && dst && numel > 0, EADGAN_ERR_INVALID, "f64_to_f32: bad arguments");
+  f64_to_f32_kernel<<<stream_grid(numel, 256), 256, 0, (cudaStream_t)stream>>>(src, dst, numel);
+  EG_LAUNCH_CHECK("f64_to_f32_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_zero_halo(void* xp, int n, int h, int w, int c, void* stream) {
+  EG_REQUIRE(xp && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0, EADGAN_ERR_INVALID,
+             "zero_halo: bad arguments (c must be a multiple of 8)");
+  const int64_t total = (int64_t)n * (2 * (w + 2) + 2 * h) * (c / 8);
+  zero_halo_kernel<<<stream_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((uint4*)xp, n, h, w, c / 8);
+  EG_LAUNCH_CHECK("zero_halo_kernel");
+  return 0;
+}

@@ -177,23 +177,58 @@ struct TcParams {
   int gemm_m, gemm_n;  // MODE_GEMM extents
   int n_store;         // real output channels (<= N_total; the rest is zero padding of the operand)
   int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
+  int m_tiles, n_tiles, parities;  // persistent tile space: tile = (parity * m_tiles + m_tile) * n_tiles + n_tile
+  int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
 };
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
+constexpr int STAT_MAX_CH = 1024;               // per-CTA running statistics cover up to this many channels
 
 template <int BLOCK_N>
 struct Cfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int TMEM_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * BLOCK_N * 16 /*stats*/;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns of ONE accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;                // two accumulators: epilogue(i) overlaps mainloop(i+1)
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int STAT_PART_BYTES = 4 * BLOCK_N * 2 * 4;   // float [4 warps][BLOCK_N][2]
+  static constexpr int STAT_ACC_BYTES = STAT_MAX_CH * 2 * 8;    // double [channels][2]
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + STAT_PART_BYTES + STAT_ACC_BYTES;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// per-channel totals over the 32 rows of a warp: butterfly transpose-reduce; lane l ends up with channel l
+template <bool SQ>
+__device__ __forceinline__ void warp_col_sums(const float* v, bool valid, int lane, float& o1, float& o2) {
+  float s1[32], s2[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = SQ ? s1[j] * s1[j] : 0.f; }
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+#pragma unroll
+    for (int j = 0; j < w; ++j) {
+      const bool up = (lane & w) != 0;
+      const float a1 = up ? s1[j] : s1[j + w], k1 = up ? s1[j + w] : s1[j];
+      s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
+      if (SQ) {
+        const float a2 = up ? s2[j] : s2[j + w], k2 = up ? s2[j + w] : s2[j];
+        s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
+      }
+    }
+  }
+  o1 = s1[0];
+  o2 = s2[0];
+}
+
 // ------------------------------------------------------------------------------------
-// fprop / dgrad / gemm kernel
+// fprop / dgrad / gemm kernel.  PERSISTENT: grid <= number of SMs, CTA c runs tiles c, c+grid, ...
+// (n-tile fastest so concurrently running CTAs share the streamed A operand through L2).
 // ------------------------------------------------------------------------------------
 template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 1)
@@ -205,21 +240,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  double* stat_smem = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + 256);  // [4][BLOCK_N]
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* stat_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
+  double* stat_acc = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::STAT_PART_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y, parity = blockIdx.z;
-  const int py = parity >> 1, px = parity & 1;
-
-  // tile origin
-  int b0 = 0, y0 = 0;
-  if (P.mode != MODE_GEMM) {
-    b0 = (m_tile / P.tiles_y) * P.Tb;
-    y0 = (m_tile % P.tiles_y) * P.Th;
-  }
-  const int n0 = n_tile * BLOCK_N;
+  const int total_tiles = P.parities * P.m_tiles * P.n_tiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -228,11 +256,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_ptr, C::TMEM_COLS);
+  }
+  if (warp >= 2 && P.want_stats) {
+    for (int i = threadIdx.x - 64; i < 2 * P.stat_channels; i += 128) stat_acc[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -243,189 +274,270 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     // ===== TMA producer =====
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < P.nkb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = tiles + stage * C::STAGE_BYTES;
-        uint8_t* sb = sa + A_BYTES;
-        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        if (P.mode == MODE_GEMM) {
-          tma_load_2d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-        } else if (P.mode == MODE_DENSE_GATHER) {
-          // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]
-          const int qi = kb % P.qblocks, tap = kb / P.qblocks;
-          tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (tap & 3), 1 + (tap >> 2), m_tile * BLOCK_M);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-        } else if (P.mode == MODE_FPROP) {
-          const int qi = kb % P.qblocks, t = kb / P.qblocks;
-          const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-          tma_load_5d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-        } else {
-          const int qi = kb % P.qblocks, t = kb / P.qblocks;  // t = ty*2+tx
-          const int ty = t >> 1, tx = t & 1;
-          const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
-          const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
-          tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, parity * P.N_total + n0);
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
+        const int m_tile = r % P.m_tiles, parity = r / P.m_tiles;
+        const int py = parity >> 1, px = parity & 1;
+        const int n0 = n_tile * BLOCK_N;
+        int b0 = 0, y0 = 0;
+        if (P.mode == MODE_FPROP || P.mode == MODE_DGRAD) {
+          b0 = (m_tile / P.tiles_y) * P.Tb;
+          y0 = (m_tile % P.tiles_y) * P.Th;
         }
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = tiles + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + A_BYTES;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (P.mode == MODE_GEMM) {
+            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+          } else if (P.mode == MODE_DENSE_GATHER) {
+            // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]
+            const int qi = kb % P.qblocks, tap = kb / P.qblocks;
+            tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (tap & 3), 1 + (tap >> 2), m_tile * BLOCK_M);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+          } else if (P.mode == MODE_FPROP) {
+            const int qi = kb % P.qblocks, t = kb / P.qblocks;
+            const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+            tma_load_5d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
+          } else {
+            const int qi = kb % P.qblocks, t = kb / P.qblocks;  // t = ty*2+tx
+            const int ty = t >> 1, tx = t & 1;
+            const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+            const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+            tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
+            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, parity * P.N_total + n0);
+          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < P.nkb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
-        const uint32_t sb = sa + A_BYTES;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          const uint64_t da = make_desc(sa + k * 32, 16, 1024);
-          const uint64_t db = make_desc(sb + k * 32, 16, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t da = make_desc(sa + k * 32, 16, 1024);
+            const uint64_t db = make_desc(sb + k * 32, 16, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == P.nkb - 1) umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == P.nkb - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
     }
   } else {
     // ===== epilogue: TMEM -> registers -> global =====
     const int quad = warp & 3;          // TMEM lane quadrant this warp may read
     const int row = quad * 32 + lane;   // row of the 128-row tile
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
+    const int et = threadIdx.x - 64;    // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
+      const int m_tile = r % P.m_tiles, parity = r / P.m_tiles;
+      const int py = parity >> 1, px = parity & 1;
+      const int n0 = n_tile * BLOCK_N;
+      int b0 = 0, y0 = 0;
+      if (P.mode == MODE_FPROP || P.mode == MODE_DGRAD) {
+        b0 = (m_tile / P.tiles_y) * P.Tb;
+        y0 = (m_tile % P.tiles_y) * P.Th;
+      }
+      bool valid;
+      int64_t out_off = 0;     // element offset of (pixel, channel n0) in the output
+      int64_t ch_stride = 1;   // element stride between channels in the output
+      int64_t mask_off = 0;
+      int bias_base = n0;      // channel index of accumulator column 0 of this tile
+      bool f32_out;
+      if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) {
+        const int m = m_tile * BLOCK_M + row;
+        valid = m < P.gemm_m;
+        if (P.mode == MODE_GEMM && P.dense_C > 0) {
+          // scatter: GEMM column n = tap * C + ch  ->  padded map [m][1+ky][1+kx][ch]
+          const int tap = n0 / P.dense_C, ch0 = n0 - tap * P.dense_C;
+          out_off = (((int64_t)m * 6 + 1 + (tap >> 2)) * 6 + 1 + (tap & 3)) * P.dense_C + ch0;
+          mask_off = out_off;
+          bias_base = ch0;
+          f32_out = false;
+        } else {
+          out_off = (int64_t)m * P.n_store + n0;
+          f32_out = true;
+        }
+      } else {
+        const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
+        const int b = b0 + bl;
+        valid = b < P.n;
+        int oy, ox;
+        if (P.mode == MODE_FPROP) { oy = y0 + yl; ox = xl; }
+        else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
+        const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
+        mask_off = pad_off;
+        f32_out = P.out_f32_nchw != 0;
+        if (f32_out) {
+          out_off = (((int64_t)b * P.n_store + n0) * P.OH + oy) * P.OW + ox;
+          ch_stride = (int64_t)P.OH * P.OW;
+        } else {
+          out_off = pad_off;
+        }
+      }
 
-    bool valid;
-    int64_t out_off = 0;     // element offset of (pixel, channel n0) in the output
-    int64_t ch_stride = 1;   // element stride between channels in the output
-    int64_t mask_off = 0;
-    int bias_base = n0;      // channel index of accumulator column 0 of this tile
-    bool f32_out;
-    if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) {
-      const int m = m_tile * BLOCK_M + row;
-      valid = m < P.gemm_m;
-      if (P.mode == MODE_GEMM && P.dense_C > 0) {
-        // scatter: GEMM column n = tap * C + ch  ->  padded map [m][1+ky][1+kx][ch]
-        const int tap = n0 / P.dense_C, ch0 = n0 - tap * P.dense_C;
-        out_off = (((int64_t)m * 6 + 1 + (tap >> 2)) * 6 + 1 + (tap & 3)) * P.dense_C + ch0;
-        mask_off = out_off;
-        bias_base = ch0;
-        f32_out = false;
-      } else {
-        out_off = (int64_t)m * P.n_store + n0;
-        f32_out = true;
-      }
-    } else {
-      const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
-      const int b = b0 + bl;
-      valid = b < P.n;
-      int oy, ox;
-      if (P.mode == MODE_FPROP) { oy = y0 + yl; ox = xl; }
-      else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
-      const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
-      mask_off = pad_off;
-      f32_out = P.out_f32_nchw != 0;
-      if (f32_out) {
-        out_off = (((int64_t)b * P.n_store + n0) * P.OH + oy) * P.OW + ox;
-        ch_stride = (int64_t)P.OH * P.OW;
-      } else {
-        out_off = pad_off;
-      }
-    }
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 
 #pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      float v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      const int n_left = P.n_store - (n0 + c0);  // real channels remaining from this column on
-      if (P.bias) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < n_left || P.dense_C > 0) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
-      }
-      if (P.want_stats) {
-        // per-channel sum / sum of squares over the 32 pixels of this warp (butterfly),
-        // lane j ends up holding channel c0+j
-        float s1[32], s2[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) { s1[j] = valid ? v[j] : 0.f; s2[j] = s1[j] * s1[j]; }
-#pragma unroll
-        for (int w = 16; w >= 1; w >>= 1) {
-#pragma unroll
-          for (int j = 0; j < w; ++j) {
-            const bool up = (lane & w) != 0;
-            const float a1 = up ? s1[j] : s1[j + w], k1 = up ? s1[j + w] : s1[j];
-            const float a2 = up ? s2[j] : s2[j + w], k2 = up ? s2[j + w] : s2[j];
-            s1[j] = k1 + __shfl_xor_sync(0xffffffffu, a1, w);
-            s2[j] = k2 + __shfl_xor_sync(0xffffffffu, a2, w);
-          }
-        }
-        // after the butterfly lane l holds the total of channel c0 + l
-        const int chl = lane;
-        stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 0] = (double)s1[0];
-        stat_smem[(quad * BLOCK_N + c0 + chl) * 2 + 1] = (double)s2[0];
-      }
-      if (valid && (n_left > 0 || P.dense_C > 0)) {
-        if (P.act != EADGAN_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = eg_act(v[j], P.act, P.slope);
-        }
-        if (P.mask_mode) {
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        const int n_left = P.n_store - (n0 + c0);  // real channels remaining from this column on
+        const bool live = valid && (n_left > 0 || P.dense_C > 0);
+        uint4 mv[4];
+        if (P.mask_mode && live) {  // issue the mask loads before waiting for the accumulator
           const uint4* mp = reinterpret_cast<const uint4*>(P.mask + mask_off + c0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const uint4 mv = __ldg(mp + g);
-            const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float m_lo = __uint_as_float(mw[e] << 16), m_hi = __uint_as_float(mw[e] & 0xffff0000u);
-              v[g * 8 + e * 2 + 0] *= eg_act_grad(m_lo, P.mask_mode, P.slope);
-              v[g * 8 + e * 2 + 1] *= eg_act_grad(m_hi, P.mask_mode, P.slope);
-            }
-          }
+          for (int g = 0; g < 4; ++g) mv[g] = __ldg(mp + g);
         }
-        if (f32_out) {
-          float* op = reinterpret_cast<float*>(P.out) + out_off + (int64_t)c0 * ch_stride;
-          if (ch_stride == 1 && n_left >= 32 && (P.n_store & 3) == 0) {
+        float v[32];
+        tmem_ld32(acc + (uint32_t)c0, v);
+        if (c0 + 32 >= BLOCK_N) {
+          // every column of this accumulator is in registers: hand the TMEM buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        if (P.bias) {
+          if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast loads
+            const float4* bp = reinterpret_cast<const float4*>(P.bias + bias_base + c0);
 #pragma unroll
-            for (int g = 0; g < 8; ++g)
-              *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            for (int g = 0; g < 8; ++g) {
+              const float4 b4 = __ldg(bp + g);
+              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
-              if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
+              if (j < n_left) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
           }
-        } else {
-          __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + out_off + c0;
+        }
+        if (P.want_stats == 1) {  // BatchNorm statistics of the pre-activation output
+          float o1, o2;
+          warp_col_sums<true>(v, valid, lane, o1, o2);
+          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
+          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = o2;
+        }
+        if (live) {
+          // the activation kind is uniform for the launch: branch ONCE, outside the element loops
+          if (P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU) {
+            const float sl = P.act == EADGAN_ACT_RELU ? 0.f : P.slope;
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t pk[4];
+            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+          } else if (P.act == EADGAN_ACT_TANH) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-              pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+          } else if (P.act == EADGAN_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          }
+          if (P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU) {
+            const float sl = P.mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                // saved OUTPUT y > 0  <=>  pre-activation > 0; bf16 sign/zero test on the raw bits
+                const bool lo_pos = (mw[e] & 0x8000u) == 0 && (mw[e] & 0x7fffu) != 0;
+                const bool hi_pos = (mw[e] & 0x80000000u) == 0 && (mw[e] & 0x7fff0000u) != 0;
+                if (!lo_pos) v[g * 8 + e * 2 + 0] *= sl;
+                if (!hi_pos) v[g * 8 + e * 2 + 1] *= sl;
+              }
             }
-            *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          } else if (P.mask_mode) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float m_lo = __uint_as_float(mw[e] << 16), m_hi = __uint_as_float(mw[e] & 0xffff0000u);
+                v[g * 8 + e * 2 + 0] *= eg_act_grad(m_lo, P.mask_mode, P.slope);
+                v[g * 8 + e * 2 + 1] *= eg_act_grad(m_hi, P.mask_mode, P.slope);
+              }
+            }
+          }
+        }
+        if (P.want_stats == 2) {  // per-channel sums of the FINAL value (bias gradient of the layer below)
+          float o1, o2;
+          warp_col_sums<false>(v, live, lane, o1, o2);
+          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
+          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = 0.f;
+        }
+        if (live) {
+          if (f32_out) {
+            float* op = reinterpret_cast<float*>(P.out) + out_off + (int64_t)c0 * ch_stride;
+            if (ch_stride == 1 && n_left >= 32 && (P.n_store & 3) == 0) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
+            }
+          } else {
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + out_off + c0;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              }
+              *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
         }
       }
+      if (P.want_stats) {
+        // fold the four warps' partials of this tile into the CTA's running per-channel totals
+        // (thread et owns channels bias_base + et, + et + 128: no conflicts, no atomics)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int ch = et; ch < BLOCK_N; ch += 128) {
+          const int gch = bias_base + ch;
+          if (gch < P.stat_channels) {
+            float a = 0.f, b2 = 0.f;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) { a += stat_part[(w * BLOCK_N + ch) * 2]; b2 += stat_part[(w * BLOCK_N + ch) * 2 + 1]; }
+            stat_acc[gch * 2 + 0] += (double)a;
+            stat_acc[gch * 2 + 1] += (double)b2;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
     }
     if (P.want_stats) {
-      // combine the four warps' partials: 128 epilogue threads, one named barrier
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int et = threadIdx.x - 64;  // 0..127
-      for (int ch = et; ch < BLOCK_N && n0 + ch < P.n_store; ch += 128) {
-        double a = 0.0, b2 = 0.0;
-#pragma unroll
-        for (int w = 0; w < 4; ++w) { a += stat_smem[(w * BLOCK_N + ch) * 2]; b2 += stat_smem[(w * BLOCK_N + ch) * 2 + 1]; }
-        atomicAdd(&P.stats[n0 + ch], a);
-        atomicAdd(&P.stats[P.N_total + n0 + ch], b2);
+      // one flush per CTA: 2 fp64 atomics per channel
+      for (int ch = et; ch < P.stat_channels; ch += 128) {
+        const double a = stat_acc[ch * 2], b2 = stat_acc[ch * 2 + 1];
+        if (a != 0.0 || b2 != 0.0) {
+          atomicAdd(&P.stats[ch], a);
+          if (P.want_stats == 1) atomicAdd(&P.stats[P.stat_channels + ch], b2);
+        }
       }
     }
   }
@@ -748,26 +860,44 @@ int pick_tile(int p, int q, int pixels, int* Tw, int* Th, int* Tb) {
 }
 
 template <int BN>
-int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid, cudaStream_t st) {
+int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     EG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     attr_set = true;
   }
+  // persistent grid: every CTA runs the same number of tiles (+-1), at most one CTA per SM
+  const int total = P.parities * P.m_tiles * P.n_tiles;
+  const int sms = eg_sm_count();
+  const int waves = (total + sms - 1) / sms;
+  const int grid = (total + waves - 1) / waves;
   tc_conv_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(ma, mb, P);
   EG_LAUNCH_CHECK("tc_conv_kernel");
   return 0;
 }
 
-int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, dim3 grid,
-                  cudaStream_t st) {
+int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& P, int m_tiles, int n_total,
+                  int parities, cudaStream_t st) {
+  P.m_tiles = m_tiles; P.n_tiles = n_total / bn; P.parities = parities;
+  EG_REQUIRE(!P.want_stats || (P.stat_channels > 0 && P.stat_channels <= STAT_MAX_CH), EADGAN_ERR_UNSUPPORTED,
+             "tc conv: fused statistics support at most %d channels (got %d)", STAT_MAX_CH, P.stat_channels);
   switch (bn) {
-    case 32: return launch_conv<32>(ma, mb, P, grid, st);
-    case 64: return launch_conv<64>(ma, mb, P, grid, st);
-    case 128: return launch_conv<128>(ma, mb, P, grid, st);
-    case 256: return launch_conv<256>(ma, mb, P, grid, st);
+    case 32: return launch_conv<32>(ma, mb, P, st);
+    case 64: return launch_conv<64>(ma, mb, P, st);
+    case 128: return launch_conv<128>(ma, mb, P, st);
+    case 256: return launch_conv<256>(ma, mb, P, st);
   }
   return eadgan_set_error(EADGAN_ERR_UNSUPPORTED, "tc conv: unsupported BLOCK_N %d", bn);
+}
+
+// BLOCK_N: 256 halves the A re-reads and the smem traffic per MAC; keep 128 while the tile count is too
+// small to fill the machine twice
+int pick_bn_tiles(int nch, int m_tiles_x_par) {
+  if (nch % 256 == 0 && (int64_t)m_tiles_x_par * (nch / 256) >= 2 * eg_sm_count()) return 256;
+  if (nch % 128 == 0) return 128;
+  if (nch % 64 == 0) return 64;
+  if (nch % 32 == 0) return 32;
+  return -1;
 }
 
 int pick_bn(int nch) {
@@ -816,23 +946,23 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
   EG_REQUIRE(x_pad && w_packed && y, EADGAN_ERR_INVALID, "tc_fprop: NULL pointer");
   const int p = d->h / 2, q = d->w / 2;
   EG_REQUIRE((2 * d->c) % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: c=%d must be a multiple of 32", d->c);
-  const int bn = pick_bn(d->k);
-  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: k=%d must be a multiple of 32", d->k);
   TcParams P{};
   P.mode = MODE_FPROP; P.n = d->n; P.p = p; P.q = q;
   EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_fprop: output map %dx%d must be a power of two <= 128 wide", p, q);
+  const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
+  const int bn = pick_bn_tiles(d->k, m_tiles);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: k=%d must be a multiple of 32", d->k);
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = d->c; P.qblocks = 2 * d->c / 64; P.nkb = 8 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
-  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k; P.stat_channels = d->k;
   EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_fprop: mask_mode without mask");
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_fprop: want_stats without stats");
   CUtensorMap ma, mb;
   if (int e = map_big_s2d(&ma, x_pad, d->n, d->c, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
   if (int e = map_matrix(&mb, w_packed, d->k, (uint64_t)16 * d->c, bn)) return e;
-  dim3 grid(((d->n + P.Tb - 1) / P.Tb) * P.tiles_y, d->k / bn, 1);
-  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+  return dispatch_conv(bn, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
 }
 
 extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed, const float* bias,
@@ -841,17 +971,19 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   EG_REQUIRE(dy_pad && w_packed && dx, EADGAN_ERR_INVALID, "tc_dgrad: NULL pointer");
   const int p = d->h / 2, q = d->w / 2;
   EG_REQUIRE(d->k % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: k=%d must be a multiple of 64", d->k);
-  const int bn = pick_bn(d->c);
-  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
   TcParams P{};
   P.mode = MODE_DGRAD; P.n = d->n; P.p = p; P.q = q;
   EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_dgrad: small map %dx%d must be a power of two <= 128 wide", p, q);
+  const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
+  const int bn = pick_bn_tiles(d->c, 4 * m_tiles);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
   P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = d->k / 64; P.nkb = 4 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
   P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
   P.n_store = (d->c_real > 0 && d->c_real < d->c) ? d->c_real : d->c;
+  P.stat_channels = P.n_store;
   EG_REQUIRE(P.n_store == d->c || d->out_f32_nchw, EADGAN_ERR_UNSUPPORTED,
              "tc_dgrad: zero-padded output channels (c_real < c) need out_f32_nchw");
   EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_dgrad: mask_mode without mask");
@@ -859,8 +991,7 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   CUtensorMap ma, mb;
   if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, P.Tw, P.Th, P.Tb)) return e;
   if (int e = map_matrix(&mb, w_packed, (uint64_t)4 * d->c, (uint64_t)4 * d->k, bn)) return e;
-  dim3 grid(((d->n + P.Tb - 1) / P.Tb) * P.tiles_y, d->c / bn, 4);
-  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+  return dispatch_conv(bn, ma, mb, P, m_tiles, d->c, 4, (cudaStream_t)stream);
 }
 
 namespace {
@@ -944,15 +1075,14 @@ extern "C" int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f
                               void* stream) {
   EG_REQUIRE(a_bf16 && b_bf16 && c_f32 && m > 0 && n > 0 && kk > 0, EADGAN_ERR_INVALID, "tc_gemm: bad arguments");
   EG_REQUIRE(kk % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: K=%d must be a multiple of 64", kk);
-  const int bn = pick_bn(n);
+  const int bn = pick_bn_tiles(n, (m + 127) / 128);
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: N=%d must be a multiple of 32", n);
   TcParams P{};
   P.mode = MODE_GEMM; P.nkb = kk / 64; P.gemm_m = m; P.gemm_n = n; P.out = c_f32; P.N_total = n; P.n_store = n;
   CUtensorMap ma, mb;
   if (int e = map_matrix(&ma, a_bf16, m, kk, 128)) return e;
   if (int e = map_matrix(&mb, b_bf16, n, kk, bn)) return e;
-  dim3 grid((m + 127) / 128, n / bn, 1);
-  return dispatch_conv(bn, ma, mb, P, grid, (cudaStream_t)stream);
+  return dispatch_conv(bn, ma, mb, P, (m + 127) / 128, n, 1, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------
@@ -991,25 +1121,24 @@ extern "C" int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, con
   CUtensorMap ma, mb;
   if (int e = map_pad6(&ma, y_pad, n, C, 128)) return e;
   if (int e = map_matrix(&mb, w_rows, 32, (uint64_t)16 * C, 32)) return e;
-  dim3 grid((n + 127) / 128, 1, 1);
-  return dispatch_conv(32, ma, mb, P, grid, (cudaStream_t)stream);
+  return dispatch_conv(32, ma, mb, P, (n + 127) / 128, 32, 1, (cudaStream_t)stream);
 }
 
 // Out[b][1+ky][1+kx][ch] (padded NHWC bf16) = (bias[ch] + sum_j A[b][j] * Wp[tap*C + ch][j]) * mask'(.)
 extern "C" int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, const float* bias, void* out_pad,
                                        const void* mask, int mask_act, float slope, int n, int C, int m_pad,
-                                       void* stream) {
+                                       double* chan_sums, void* stream) {
   EG_REQUIRE(a_bf16 && w_cols && out_pad && n > 0, EADGAN_ERR_INVALID, "tc_dense_scatter: bad arguments");
   EG_REQUIRE(C % 128 == 0 && m_pad % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_dense_scatter: needs C%%128==0, m_pad%%64==0");
   TcParams P{};
   P.mode = MODE_GEMM; P.nkb = m_pad / 64; P.gemm_m = n; P.gemm_n = 16 * C; P.N_total = 16 * C; P.n_store = 16 * C;
   P.dense_C = C; P.bias = bias; P.out = out_pad; P.mask = (const __nv_bfloat16*)mask; P.mask_mode = mask ? mask_act : 0;
   P.slope = slope;
+  if (chan_sums) { P.want_stats = 2; P.stats = chan_sums; P.stat_channels = C; }
   CUtensorMap ma, mb;
   if (int e = map_matrix(&ma, a_bf16, n, m_pad, 128)) return e;
   if (int e = map_matrix(&mb, w_cols, (uint64_t)16 * C, m_pad, 128)) return e;
-  dim3 grid((n + 127) / 128, 16 * C / 128, 1);
-  return dispatch_conv(128, ma, mb, P, grid, (cudaStream_t)stream);
+  return dispatch_conv(128, ma, mb, P, (n + 127) / 128, 16 * C, 1, (cudaStream_t)stream);
 }
 
 extern "C" size_t eadgan_tc_dense_wgrad_workspace(int C, int m_pad) {

@@ -10,9 +10,14 @@ from . import _lib as L
 from ._lib import ACT_NONE, call, ptr, stream, t4
 
 
-def alloc_padded(n, h, w, c, device):
-    """[n, h+2, w+2, c] bf16 with a zero halo (interior is written by a kernel epilogue)."""
-    return torch.zeros((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
+def alloc_padded(n, h, w, c, device, zero_interior=False):
+    """[n, h+2, w+2, c] bf16 with a zero halo.  The interior is left uninitialised unless
+    ``zero_interior`` (every producing kernel overwrites it completely); only the halo is cleared."""
+    if zero_interior or c % 8 != 0:
+        return torch.zeros((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
+    xp = torch.empty((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
+    call("eadgan_zero_halo", ptr(xp), n, h, w, c, stream())
+    return xp
 
 
 def interior(xp):
@@ -24,7 +29,7 @@ def interior(xp):
 def to_padded(x, c_alloc=None):
     """fp32/bf16 NCHW tensor -> padded NHWC bf16 (copy4 kernel); channels zero-padded to c_alloc."""
     n, c, h, w = x.shape
-    xp = alloc_padded(n, h, w, c_alloc or c, x.device)
+    xp = alloc_padded(n, h, w, c_alloc or c, x.device, zero_interior=bool(c_alloc) and c_alloc != c)
     src, dst = t4(x), t4(interior(xp)[:, :c])
     call("eadgan_copy4", C.byref(src), C.byref(dst), n, c, h, w, stream())
     return xp
@@ -64,11 +69,11 @@ def _desc(n, c, h, w, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, want_stats
 
 
 def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
-          out=None):
+          out=None, stats_mode=1):
     """big map xp [n,h+2,w+2,c] -> small map [n,p+2,q+2,k] (or fp32 NCHW [n,k,p,q])."""
     n, hp, wp, c = xp.shape
     h, w = hp - 2, wp - 2
-    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode)
+    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats_mode if stats is not None else 0, mask_mode)
     if out is None:
         out = (torch.empty((n, k, h // 2, w // 2), device=xp.device, dtype=torch.float32) if out_f32_nchw
                else alloc_padded(n, h // 2, w // 2, k, xp.device))
@@ -77,11 +82,11 @@ def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=No
 
 
 def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
-          out=None, c_real=0):
+          out=None, c_real=0, stats_mode=1):
     """small map yp [n,p+2,q+2,k] -> big map [n,2p+2,2q+2,c] (or fp32 NCHW [n,c_real or c,2p,2q])."""
     n, pp, qp, k = yp.shape
     h, w = 2 * (pp - 2), 2 * (qp - 2)
-    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats is not None, mask_mode, c_real)
+    d = _desc(n, c, h, w, k, act, slope, out_f32_nchw, stats_mode if stats is not None else 0, mask_mode, c_real)
     if out is None:
         out = (torch.empty((n, c_real or c, h, w), device=yp.device, dtype=torch.float32) if out_f32_nchw
                else alloc_padded(n, h, w, c, yp.device))
@@ -116,11 +121,11 @@ def dense_gather(yp, w_rows, bias, m_real):
     return out
 
 
-def dense_scatter(a, w_cols, bias, Cc, mask=None, mask_act=0, slope=0.0):
+def dense_scatter(a, w_cols, bias, Cc, mask=None, mask_act=0, slope=0.0, chan_sums=None):
     n, m_pad = a.shape
     out = alloc_padded(n, 4, 4, Cc, a.device)
     call("eadgan_tc_dense_scatter", ptr(a), ptr(w_cols), ptr(bias), ptr(out), ptr(mask), int(mask_act), float(slope),
-         n, Cc, m_pad, stream())
+         n, Cc, m_pad, ptr(chan_sums), stream())
     return out
 
 

@@ -117,7 +117,10 @@ typedef struct {
   float slope;
   int32_t out_f32_nchw; /* 1: write the result as dense fp32 NCHW instead of padded NHWC bf16 */
   int32_t want_stats;   /* 1: accumulate per-channel sum / sum-of-squares of the pre-activation
-                              output into fp64 stats[2*C] (BatchNorm statistics fused in the epilogue) */
+                              output into fp64 stats[2*C] (BatchNorm statistics fused in the epilogue);
+                           2: accumulate per-channel sums of the FINAL value (after activation / mask) into
+                              fp64 stats[C] -- the bias gradient of the layer below, fused into the kernel
+                              that produces that layer's output gradient */
   int32_t c_real;       /* 0 or c: all big-map channels are real.  0 < c_real < c: channels >= c_real of the
                               big map are zero padding (the 3-channel image layers run with c = 32); weights
                               are given / returned as [k, c_real, 4, 4] */
@@ -160,6 +163,7 @@ int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, const float* b
                            int C, int m_real, void* stream);
 int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, const float* bias, void* out_pad,
                             const void* mask, int mask_act, float slope, int n, int C, int m_pad,
+                            double* chan_sums /* NULL, or fp64 [C]: per-channel sums of the result */,
                             void* stream);
 size_t eadgan_tc_dense_wgrad_workspace(int C, int m_pad);
 int eadgan_tc_dense_wgrad(const void* a_bf16, const void* y_pad, float* dw, void* workspace,
@@ -287,6 +291,10 @@ int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, d
 
 /* fill / scale helpers used by the host layer (buffer zeroing stays on our stream) */
 int eadgan_fill_f32(float* p, int64_t numel, float value, void* stream);
+int eadgan_f64_to_f32(const double* src, float* dst, int64_t numel, void* stream);
+/* zero the 1-pixel halo of a padded NHWC bf16 buffer [n, h+2, w+2, c] (c % 8 == 0); the interior is
+ * left untouched (it is fully overwritten by the producing kernel's epilogue) */
+int eadgan_zero_halo(void* xp, int n, int h, int w, int c, void* stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,7 @@ def phase_errors(names, ours_grads, ref_grads):
             sib = n[:-5] + ".weight"
         if sib is not None:
             floor = refs[sib].abs().max().item()
-            out[n] = (tensor_err(a, b, floor), None, None)
+            out[n] = (tensor_err(a, b, floor), None, None if n in ZERO_GRAD else "small")
         else:
             out[n] = (tensor_err(a, b), l2_err(a, b), cosine(a, b))
     return out

@@ -90,6 +90,8 @@ def test_celeba_step_bf16(cuda, B):
         for n, (mx, l2, cs) in errs.items():
             if cs is None:
                 assert mx <= 2e-2, (ph, n, mx)      # zero-gradient biases: closed form, exact
+            elif cs == "small":
+                assert mx <= 0.15, (ph, n, mx)      # [3]-element bias, normalised by its layer's weight gradient
             else:
                 assert cs >= 0.95, (ph, n, cs)
                 assert l2 <= 0.35, (ph, n, l2)

@@ -31,7 +31,7 @@ for prec in precs:
         er = U.phase_errors(names[ph], r32["phases"][ph]["grads"], ref["phases"][ph]["grads"]) if ph == 0 else None
         mx = [v[0] for v in eo.values()]
         l2 = [v[1] for v in eo.values() if v[1] is not None]
-        cs = [v[2] for v in eo.values() if v[2] is not None]
+        cs = [v[2] for v in eo.values() if isinstance(v[2], float)]
         print(f"  phase {ph} ours-{prec} vs fp64: max-err max {max(mx):.2e} median {sorted(mx)[len(mx)//2]:.2e} | "
               f"L2 max {max(l2):.2e} median {sorted(l2)[len(l2)//2]:.2e} | cos min {min(cs):.5f}")
         if er is not None:
