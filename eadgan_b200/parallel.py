@@ -33,7 +33,7 @@ class DataParallel:
     def __init__(self, rank, world_size, device, bucket_bytes=32 << 20, overlap=True):
         self.rank, self.world_size, self.device = rank, world_size, device
         self.bucket_elems = max(1, bucket_bytes // 4)
-        self.overlap = overlap and device.type == "cuda"
+        self.overlap = overlap  # on CPU (gloo, tests) the buckets are reduced asynchronously too, without a side stream
         self.comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
         self._plans = {}      # id(optimizer) -> plan
         self._armed = None
