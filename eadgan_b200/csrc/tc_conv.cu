@@ -28,6 +28,7 @@
 #include <cuda.h>
 
 #include <mutex>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -186,13 +187,15 @@ constexpr int BLOCK_K = 64;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int STAT_MAX_CH = 1024;               // per-CTA running statistics cover up to this many channels
 
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>   // MT = number of 128-row M tiles per CTA tile (1 or 2): MT = 2 halves the B re-reads
 struct Cfg {
   static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
-  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns of ONE accumulator
-  static constexpr int TMEM_COLS = 2 * ACC_COLS;                // two accumulators: epilogue(i) overlaps mainloop(i+1)
+  static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES < 8 ? (192 * 1024) / STAGE_BYTES : 8;
+  static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns of ONE 128-row accumulator
+  static constexpr int BUF_COLS = MT * ACC_COLS;                // one accumulator buffer (MT sub-tiles)
+  static constexpr int TMEM_COLS = 2 * BUF_COLS;                // two buffers: epilogue(i) overlaps mainloop(i+1)
+  static_assert(TMEM_COLS <= 512, "accumulators exceed tensor memory");
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAT_PART_BYTES = 4 * BLOCK_N * 2 * 4;   // float [4 warps][BLOCK_N][2]
   static constexpr int STAT_ACC_BYTES = STAT_MAX_CH * 2 * 8;    // double [channels][2]
@@ -230,11 +233,11 @@ __device__ __forceinline__ void warp_col_sums(const float* v, bool valid, int la
 // fprop / dgrad / gemm kernel.  PERSISTENT: grid <= number of SMs, CTA c runs tiles c, c+grid, ...
 // (n-tile fastest so concurrently running CTAs share the streamed A operand through L2).
 // ------------------------------------------------------------------------------------
-template <int BLOCK_N>
+template <int BLOCK_N, int MT>
 __global__ void __launch_bounds__(192, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams P) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, MT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* tiles = smem;
@@ -276,40 +279,39 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
-        const int m_tile = r % P.m_tiles, parity = r / P.m_tiles;
+        const int m_grp = r % P.m_tiles, parity = r / P.m_tiles;   // m_grp: group of MT consecutive 128-row tiles
         const int py = parity >> 1, px = parity & 1;
         const int n0 = n_tile * BLOCK_N;
-        int b0 = 0, y0 = 0;
-        if (P.mode == MODE_FPROP || P.mode == MODE_DGRAD) {
-          b0 = (m_tile / P.tiles_y) * P.Tb;
-          y0 = (m_tile % P.tiles_y) * P.Th;
-        }
         for (int kb = 0; kb < P.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
-          uint8_t* sb = sa + A_BYTES;
+          uint8_t* sb = sa + MT * A_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          if (P.mode == MODE_GEMM) {
-            tma_load_2d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-          } else if (P.mode == MODE_DENSE_GATHER) {
-            // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]
-            const int qi = kb % P.qblocks, tap = kb / P.qblocks;
-            tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (tap & 3), 1 + (tap >> 2), m_tile * BLOCK_M);
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-          } else if (P.mode == MODE_FPROP) {
-            const int qi = kb % P.qblocks, t = kb / P.qblocks;
-            const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-            tma_load_5d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, n0);
-          } else {
-            const int qi = kb % P.qblocks, t = kb / P.qblocks;  // t = ty*2+tx
-            const int ty = t >> 1, tx = t & 1;
-            const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
-            const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
-            tma_load_4d(sa, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
-            tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K, parity * P.N_total + n0);
+          const int qi = kb % P.qblocks, t = kb / P.qblocks;
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {
+            const int m_tile = m_grp * MT + h;
+            uint8_t* sah = sa + h * A_BYTES;
+            if (P.mode == MODE_GEMM) {
+              tma_load_2d(sah, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+            } else if (P.mode == MODE_DENSE_GATHER) {
+              // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]  (t = tap)
+              tma_load_4d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (t & 3), 1 + (t >> 2), m_tile * BLOCK_M);
+            } else {
+              const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
+              if (P.mode == MODE_FPROP) {
+                const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+                tma_load_5d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
+              } else {  // t = ty*2+tx
+                const int ty = t >> 1, tx = t & 1;
+                const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+                const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+                tma_load_4d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
+              }
+            }
           }
+          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K,
+                      (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -323,18 +325,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const int buf = it & 1;
       mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::ACC_COLS);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * C::BUF_COLS);
       for (int kb = 0; kb < P.nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t sa = smem_u32(tiles + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + A_BYTES;
+          const uint32_t sb = sa + MT * A_BYTES;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t da = make_desc(sa + k * 32, 16, 1024);
             const uint64_t db = make_desc(sb + k * 32, 16, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              const uint64_t da = make_desc(sa + h * A_BYTES + k * 32, 16, 1024);
+              umma_bf16(d_tmem + (uint32_t)(h * C::ACC_COLS), da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
           }
           umma_commit(&empty_bar[stage]);
           if (kb == P.nkb - 1) umma_commit(&tmem_full_bar[buf]);
@@ -351,9 +356,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
-      const int m_tile = r % P.m_tiles, parity = r / P.m_tiles;
+      const int m_grp = r % P.m_tiles, parity = r / P.m_tiles;
       const int py = parity >> 1, px = parity & 1;
       const int n0 = n_tile * BLOCK_N;
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int h = 0; h < MT; ++h) {
+      const int m_tile = m_grp * MT + h;
       int b0 = 0, y0 = 0;
       if (P.mode == MODE_FPROP || P.mode == MODE_DGRAD) {
         b0 = (m_tile / P.tiles_y) * P.Tb;
@@ -397,10 +408,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
       }
 
-      const int buf = it & 1;
-      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
-      tc_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
+      const uint32_t acc = tmem_base + (uint32_t)(buf * C::BUF_COLS + h * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -414,7 +422,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         float v[32];
         tmem_ld32(acc + (uint32_t)c0, v);
-        if (c0 + 32 >= BLOCK_N) {
+        if (c0 + 32 >= BLOCK_N && h == MT - 1) {
           // every column of this accumulator is in registers: hand the TMEM buffer back to the MMA warp
           tc_fence_before();
           __syncwarp();
@@ -529,6 +537,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
       }
+      }  // sub-tile h
     }
     if (P.want_stats) {
       // one flush per CTA: 2 fp64 atomics per channel
@@ -859,11 +868,11 @@ int pick_tile(int p, int q, int pixels, int* Tw, int* Th, int* Tb) {
   return 0;
 }
 
-template <int BN>
+template <int BN, int MT>
 int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    EG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::SMEM));
     attr_set = true;
   }
   // persistent grid: every CTA runs the same number of tiles (+-1), at most one CTA per SM
@@ -871,21 +880,27 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P,
   const int sms = eg_sm_count();
   const int waves = (total + sms - 1) / sms;
   const int grid = (total + waves - 1) / waves;
-  tc_conv_kernel<BN><<<grid, 192, Cfg<BN>::SMEM, st>>>(ma, mb, P);
+  tc_conv_kernel<BN, MT><<<grid, 192, Cfg<BN, MT>::SMEM, st>>>(ma, mb, P);
   EG_LAUNCH_CHECK("tc_conv_kernel");
   return 0;
 }
 
 int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& P, int m_tiles, int n_total,
                   int parities, cudaStream_t st) {
-  P.m_tiles = m_tiles; P.n_tiles = n_total / bn; P.parities = parities;
+  // two 128-row tiles per CTA tile (sharing every B load) when BLOCK_N <= 128 and there is enough work
+  int mt = (bn <= 128 && (int64_t)m_tiles * parities * (n_total / bn) >= 4 * eg_sm_count()) ? 2 : 1;
+  if (const char* e = getenv("EADGAN_TC_MT")) { if (bn <= 128 && atoi(e) >= 1 && atoi(e) <= 2) mt = atoi(e); }
+  P.m_tiles = (m_tiles + mt - 1) / mt; P.n_tiles = n_total / bn; P.parities = parities;
   EG_REQUIRE(!P.want_stats || (P.stat_channels > 0 && P.stat_channels <= STAT_MAX_CH), EADGAN_ERR_UNSUPPORTED,
              "tc conv: fused statistics support at most %d channels (got %d)", STAT_MAX_CH, P.stat_channels);
-  switch (bn) {
-    case 32: return launch_conv<32>(ma, mb, P, st);
-    case 64: return launch_conv<64>(ma, mb, P, st);
-    case 128: return launch_conv<128>(ma, mb, P, st);
-    case 256: return launch_conv<256>(ma, mb, P, st);
+  switch (bn * 10 + mt) {
+    case 321: return launch_conv<32, 1>(ma, mb, P, st);
+    case 322: return launch_conv<32, 2>(ma, mb, P, st);
+    case 641: return launch_conv<64, 1>(ma, mb, P, st);
+    case 642: return launch_conv<64, 2>(ma, mb, P, st);
+    case 1281: return launch_conv<128, 1>(ma, mb, P, st);
+    case 1282: return launch_conv<128, 2>(ma, mb, P, st);
+    case 2561: return launch_conv<256, 1>(ma, mb, P, st);
   }
   return eadgan_set_error(EADGAN_ERR_UNSUPPORTED, "tc conv: unsupported BLOCK_N %d", bn);
 }
@@ -893,6 +908,10 @@ int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, TcParams
 // BLOCK_N: 256 halves the A re-reads and the smem traffic per MAC; keep 128 while the tile count is too
 // small to fill the machine twice
 int pick_bn_tiles(int nch, int m_tiles_x_par) {
+  if (const char* e = getenv("EADGAN_TC_BN")) {  // experiments only (tools/bench_gemm.py)
+    const int bn = atoi(e);
+    if (bn > 0 && nch % bn == 0) return bn;
+  }
   if (nch % 256 == 0 && (int64_t)m_tiles_x_par * (nch / 256) >= 2 * eg_sm_count()) return 256;
   if (nch % 128 == 0) return 128;
   if (nch % 64 == 0) return 64;
@@ -1008,11 +1027,24 @@ int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
   P->steps_total = ((d->n + P->Tb - 1) / P->Tb) * P->tiles_y;
   *bn = (P->Ktot % 256 == 0) ? 256 : (P->Ktot % 128 == 0 ? 128 : 64);
   const int tiles = (P->Ktot / *bn) * ((d->k + 127) / 128);
-  int s = (2 * eg_sm_count() + tiles - 1) / tiles;
+  // split of the pixel reduction: one CTA per (tile, split) and one CTA per SM at a time, so the kernel runs in
+  // waves of sm_count CTAs.  Pick the split count minimising  waves * steps_per_split  (tensor time, a 64-pixel
+  // step of a 128 x bn tile is bn*2 clocks) plus the fp32 partial-sum traffic (written once, read once).
+  const int sms = eg_sm_count();
   const int max_s = (P->steps_total + 7) / 8;
-  if (s > max_s) s = max_s;
-  if (s < 1) s = 1;
-  P->steps_per_split = (P->steps_total + s - 1) / s;
+  const int k_pad = ((d->k + 127) / 128) * 128;
+  double best = 1e300;
+  int best_s = 1;
+  for (int s = 1; s <= max_s && s <= 4 * sms; ++s) {
+    const int sps = (P->steps_total + s - 1) / s;
+    const int s_eff = (P->steps_total + sps - 1) / sps;
+    const int64_t ctas = (int64_t)tiles * s_eff;
+    const int64_t waves = (ctas + sms - 1) / sms;
+    const double t_mma = (double)waves * (sps * (*bn) * 2.0 + 6000.0) / 1.9e9 / 0.9;  // + per-CTA prologue/epilogue
+    const double t_part = (double)s_eff * k_pad * (double)P->Ktot * 8.0 / 6.0e12;
+    if (t_mma + t_part < best) { best = t_mma + t_part; best_s = s_eff; }
+  }
+  P->steps_per_split = (P->steps_total + best_s - 1) / best_s;
   *splits = (P->steps_total + P->steps_per_split - 1) / P->steps_per_split;
   return 0;
 }
