@@ -89,6 +89,8 @@ _PROTOS = {
     "eadgan_mi_fwd": [_P, _P, _I, _I, _P, _P],
     "eadgan_mi_bwd": [_P, _P, _P, _I, _I, _P, _P],
     "eadgan_adam_step": [C.POINTER(AdamTensors), _D, _D, _D, _D, _D, _F, _P],
+    "eadgan_adam_step_dev": [C.POINTER(AdamTensors), _D, _D, _D, _D, _P, _F, _P],
+    "eadgan_adam_advance": [_P, _P],
     "eadgan_fill_f32": [_P, _L, _F, _P],
     "eadgan_f64_to_f32": [_P, _P, _L, _P],
     "eadgan_zero_halo": [_P, _I, _I, _I, _I, _P],
@@ -100,6 +102,7 @@ _SPECIAL = {
     "eadgan_kernel_launches": ([], C.c_int64),
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
     "eadgan_tc_dense_wgrad_workspace": ([_I, _I], C.c_size_t),
+    "eadgan_spectral_norm_scratch_floats": ([_I, _I, _I], C.c_size_t),
 }
 EXPORTED = sorted(list(_PROTOS) + list(_SPECIAL))
 

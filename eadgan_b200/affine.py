@@ -37,16 +37,33 @@ def celeba_matrix(code5):
                        code5[:, 3] * 0.1, code5[:, 4] * 0.1)
 
 
+def _rzt_parts(code5):
+    """(a, b, c, d, tx, ty) of [[a, b, tx], [c, d, ty], [0, 0, 1]] = R(theta) diag(p, q, 1) T(x, y)."""
+    theta, p, q = code5[:, 0] * (math.pi / 9), code5[:, 1] * 0.2 + 1, code5[:, 2] * 0.2 + 1
+    x, y = code5[:, 3] * 0.1, code5[:, 4] * 0.1
+    c, s = torch.cos(theta), torch.sin(theta)
+    a, b, cc, d = c * p, -s * q, s * p, c * q
+    return a, b, cc, d, a * x + b * y, cc * x + d * y
+
+
 def celeba_relative_code(real_code, trans_code):
-    """affine_regularzier of celebA/utils_rpqxy.py:82-116."""
-    rel = celeba_matrix(trans_code[:, :5]) @ torch.linalg.inv(celeba_matrix(real_code[:, :5]))
-    a, b, c, d = rel[:, 0, 0], rel[:, 0, 1], rel[:, 1, 0], rel[:, 1, 1]
+    """affine_regularzier of celebA/utils_rpqxy.py:82-116.  rel = M(trans) @ inverse(M(real)); both are
+    affine (last row 0 0 1), so the inverse is written in closed form -- torch.inverse / linalg.inv check
+    for singularity on the HOST (a device->host sync in the middle of every step)."""
+    a1, b1, c1, d1, x1, y1 = _rzt_parts(real_code[:, :5])
+    a2, b2, c2, d2, x2, y2 = _rzt_parts(trans_code[:, :5])
+    det = a1 * d1 - b1 * c1
+    ia, ib, ic, id_ = d1 / det, -b1 / det, -c1 / det, a1 / det          # inverse of the 2x2 block
+    itx, ity = -(ia * x1 + ib * y1), -(ic * x1 + id_ * y1)               # inverse translation
+    a, b = a2 * ia + b2 * ic, a2 * ib + b2 * id_
+    c, d = c2 * ia + d2 * ic, c2 * ib + d2 * id_
+    tx, ty = a2 * itx + b2 * ity + x2, c2 * itx + d2 * ity + y2
     th = 0.5 * torch.atan(2 * (a * c - b * d) / (a * a + d * d - b * b - c * c))
     ct, st = torch.cos(th), torch.sin(th)
     p = a * ct + c * st
     q = -b * st + d * ct
-    x = (rel[:, 0, 2] * ct + rel[:, 1, 2] * st) / p
-    y = (rel[:, 1, 2] * ct - rel[:, 0, 2] * st) / q
+    x = (tx * ct + ty * st) / p
+    y = (ty * ct - tx * st) / q
     return torch.stack((th * (9 / math.pi), (p - 1) / 0.2, (q - 1) / 0.2, x / 0.1, y / 0.1), dim=1)
 
 

@@ -142,8 +142,17 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   p = __fadd_rn(p, __fdiv_rn(__fmul_rn(neg_step, m), denom));
 }
 
+// step_dev != NULL: the step count lives on the device (CUDA-graph replays advance it with
+// adam_advance_kernel); the bias corrections are then formed here, in double, exactly like the host path
 __global__ void __launch_bounds__(256) adam_kernel(const AdamLaunch L, float w1, float beta2, float w2, float eps,
-                                                   float neg_step, float bc2_sqrt, float gscale) {
+                                                   float neg_step, float bc2_sqrt, float gscale,
+                                                   const int64_t* __restrict__ step_dev, double lr, double beta1d,
+                                                   double beta2d) {
+  if (step_dev) {
+    const double t = (double)*step_dev;
+    neg_step = (float)(-(lr / (1.0 - pow(beta1d, t))));
+    bc2_sqrt = (float)sqrt(1.0 - pow(beta2d, t));
+  }
   int ti = 0;
   while (ti + 1 < L.t.count && (int)blockIdx.x >= L.blk_start[ti + 1]) ++ti;
   const int64_t off = (int64_t)(blockIdx.x - L.blk_start[ti]) * ADAM_CHUNK;
@@ -184,6 +193,8 @@ __global__ void __launch_bounds__(256) adam_kernel(const AdamLaunch L, float w1,
     }
   }
 }
+
+__global__ void adam_advance_kernel(int64_t* step_dev) { *step_dev += 1; }
 
 }  // namespace
 
@@ -250,8 +261,9 @@ extern "C" int eadgan_mi_bwd(const float* q, const float* c, const float* gout, 
   return 0;
 }
 
-extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, double eps,
-                                double step_size, double bc2_sqrt, float grad_scale, void* stream) {
+namespace {
+int adam_launch(const eadgan_adam_tensors* t, double beta1, double beta2, double eps, double step_size,
+                double bc2_sqrt, float grad_scale, const int64_t* step_dev, double lr, void* stream) {
   EG_REQUIRE(t && t->count > 0 && t->count <= EADGAN_ADAM_MAX_TENSORS, EADGAN_ERR_INVALID,
              "adam_step: tensor count must be in [1, %d]", EADGAN_ADAM_MAX_TENSORS);
   AdamLaunch L;
@@ -267,7 +279,27 @@ extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, doub
   // scalars are rounded to fp32 exactly where torch rounds its Python doubles: 1-beta1 and
   // 1-beta2 are formed in double first (1 - 0.999 != 1.f - 0.999f)
   adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(L, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
-                                                        (float)eps, (float)(-step_size), (float)bc2_sqrt, grad_scale);
+                                                        (float)eps, (float)(-step_size), (float)bc2_sqrt, grad_scale,
+                                                        step_dev, lr, beta1, beta2);
   EG_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+}  // namespace
+
+extern "C" int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, double eps,
+                                double step_size, double bc2_sqrt, float grad_scale, void* stream) {
+  return adam_launch(t, beta1, beta2, eps, step_size, bc2_sqrt, grad_scale, nullptr, 0.0, stream);
+}
+
+extern "C" int eadgan_adam_step_dev(const eadgan_adam_tensors* t, double beta1, double beta2, double eps, double lr,
+                                    const int64_t* step_dev, float grad_scale, void* stream) {
+  EG_REQUIRE(step_dev != nullptr, EADGAN_ERR_INVALID, "adam_step_dev: NULL step counter");
+  return adam_launch(t, beta1, beta2, eps, 0.0, 1.0, grad_scale, step_dev, lr, stream);
+}
+
+extern "C" int eadgan_adam_advance(int64_t* step_dev, void* stream) {
+  EG_REQUIRE(step_dev != nullptr, EADGAN_ERR_INVALID, "adam_advance: NULL step counter");
+  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+  EG_LAUNCH_CHECK("adam_advance_kernel");
   return 0;
 }

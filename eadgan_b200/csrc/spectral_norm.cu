@@ -10,7 +10,7 @@
 
 namespace {
 
-// t[j] += sum_{i in row range} W[i,j] * u[i];  block = 128 threads = 128 columns
+// t[split][j] = sum_{i in row range of split} W[i,j] * u[i];  block = 128 threads = 128 columns
 __global__ void __launch_bounds__(128) sn_wtu_kernel(const float* __restrict__ W, const float* __restrict__ u,
                                                      float* __restrict__ t, int rows, int cols, int rows_per_blk) {
   const int j = blockIdx.x * 128 + threadIdx.x;
@@ -26,15 +26,21 @@ __global__ void __launch_bounds__(128) sn_wtu_kernel(const float* __restrict__ W
     acc = fmaf(a2, u[i + 2], acc); acc = fmaf(a3, u[i + 3], acc);
   }
   for (; i < r1; ++i) acc = fmaf(W[(int64_t)i * cols + j], u[i], acc);
-  if (gridDim.y == 1) t[j] = acc; else atomicAdd(&t[j], acc);
+  t[(int64_t)blockIdx.y * cols + j] = acc;   // per-split partial: summed in a fixed order by sn_normalize_kernel
 }
 
-// single block: out[i] = in[i] / max(||in||, eps)
-__global__ void __launch_bounds__(1024) sn_normalize_kernel(const float* __restrict__ in, float* __restrict__ out,
-                                                            int n, float eps) {
+// single block: x = sum over `parts` partial vectors (fixed order: deterministic); out = x / max(||x||, eps).
+// `in` is overwritten with x in its first n entries.
+__global__ void __launch_bounds__(1024) sn_normalize_kernel(float* __restrict__ in, float* __restrict__ out,
+                                                            int n, int parts, float eps) {
   __shared__ float red[32];
   float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) s = fmaf(in[i], in[i], s);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float x = in[i];
+    for (int p = 1; p < parts; ++p) x += in[(int64_t)p * n + i];
+    in[i] = x;
+    s = fmaf(x, x, s);
+  }
   s = eg_block_sum(s, red);
   const float inv = 1.f / fmaxf(sqrtf(s), eps);
   for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i] * inv;
@@ -94,28 +100,52 @@ __global__ void __launch_bounds__(256) sn_scale_kernel(const float* __restrict__
   }
 }
 
-// acc[0] += <a, b>
+// part[block] = <a, b> over the block's grid-stride slice (no atomics: the total is summed in a fixed order)
 __global__ void __launch_bounds__(256) sn_dot_kernel(const float* __restrict__ a, const float* __restrict__ b,
-                                                     int64_t n, float* __restrict__ acc) {
+                                                     int64_t n, float* __restrict__ part) {
   __shared__ float red[32];
   float s = 0.f;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
-    s = fmaf(a[i], b[i], s);
+  if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
+      s = fmaf(x.x, y.x, s); s = fmaf(x.y, y.y, s); s = fmaf(x.z, y.z, s); s = fmaf(x.w, y.w, s);
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+      s = fmaf(a[i], b[i], s);
+  }
   s = eg_block_sum(s, red);
-  if (threadIdx.x == 0) atomicAdd(acc, s);
+  if (threadIdx.x == 0) part[blockIdx.x] = s;
 }
 
-// dW_orig[i,j] = dW[i,j]/sigma - (dot/sigma^2) * u[i] * v[j]
+// dW_orig[i,j] = dW[i,j]/sigma - (dot/sigma^2) * u[i] * v[j];  dot = sum of nparts partials (every block
+// re-sums them in the same order); one block row-slice at a time so u[r] is a scalar per row
 __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ dW, const float* __restrict__ u,
                                                      const float* __restrict__ v, const float* __restrict__ sigma,
-                                                     const float* __restrict__ dot, int rows, int cols,
+                                                     const float* __restrict__ part, int nparts, int rows, int cols,
                                                      float* __restrict__ out) {
+  __shared__ float red[32];
+  float d = 0.f;
+  for (int i = threadIdx.x; i < nparts; i += blockDim.x) d += part[i];
+  d = eg_block_sum(d, red);
   const float sg = *sigma;
-  const float coef = *dot / (sg * sg);
+  const float coef = d / (sg * sg);
   const int64_t n = (int64_t)rows * cols;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
-    out[i] = dW[i] / sg - coef * u[r] * v[c];
+  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(dW) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+    const int cv = cols >> 2;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / cv), c4 = (int)(i - (int64_t)r * cv);
+      const float4 g = reinterpret_cast<const float4*>(dW)[i], vv = reinterpret_cast<const float4*>(v)[c4];
+      const float cu = coef * u[r];
+      float4 o;
+      o.x = g.x / sg - cu * vv.x; o.y = g.y / sg - cu * vv.y; o.z = g.z / sg - cu * vv.z; o.w = g.w / sg - cu * vv.w;
+      reinterpret_cast<float4*>(out)[i] = o;
+    }
+  } else {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+      out[i] = dW[i] / sg - coef * u[r] * v[c];
+    }
   }
 }
 
@@ -133,20 +163,19 @@ extern "C" int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols,
   EG_REQUIRE(w_orig && u && v && sigma && scratch && rows > 0 && cols > 0, EADGAN_ERR_INVALID,
              "spectral_norm_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
-  float* t = scratch;          // [cols]
-  float* s = scratch + cols;   // [rows]
+  int col_tiles = (cols + 127) / 128;
+  int splits = (4 * eg_sm_count() + col_tiles - 1) / col_tiles;
+  int max_splits = (rows + 15) / 16;
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int rpb = (rows + splits - 1) / splits;
+  splits = (rows + rpb - 1) / rpb;
+  float* s = scratch;          // [rows]
+  float* t = scratch + rows;   // [splits][cols] partials of W^T u
   if (do_power_iter) {
-    int col_tiles = (cols + 127) / 128;
-    int splits = (4 * eg_sm_count() + col_tiles - 1) / col_tiles;
-    int max_splits = (rows + 15) / 16;
-    if (splits > max_splits) splits = max_splits;
-    if (splits < 1) splits = 1;
-    const int rpb = (rows + splits - 1) / splits;
-    splits = (rows + rpb - 1) / rpb;
-    if (splits > 1) EG_CUDA(cudaMemsetAsync(t, 0, sizeof(float) * cols, st));
     sn_wtu_kernel<<<dim3(col_tiles, splits), 128, 0, st>>>(w_orig, u, t, rows, cols, rpb);
     EG_LAUNCH_CHECK("sn_wtu_kernel");
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(t, v, cols, eps);
+    sn_normalize_kernel<<<1, 1024, 0, st>>>(t, v, cols, splits, eps);
     EG_LAUNCH_CHECK("sn_normalize_kernel");
   }
   sn_wv_kernel<<<rows, 256, 0, st>>>(w_orig, v, s, rows, cols);
@@ -168,10 +197,16 @@ extern "C" int eadgan_spectral_norm_bwd(const float* dw_sn, const float* w_orig,
              EADGAN_ERR_INVALID, "spectral_norm_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)rows * cols;
-  EG_CUDA(cudaMemsetAsync(scratch, 0, sizeof(float), st));
-  sn_dot_kernel<<<grid_for(n), 256, 0, st>>>(dw_sn, w_orig, n, scratch);
+  const int parts = grid_for(n);
+  sn_dot_kernel<<<parts, 256, 0, st>>>(dw_sn, w_orig, n, scratch);
   EG_LAUNCH_CHECK("sn_dot_kernel");
-  sn_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dw_sn, u, v, sigma, scratch, rows, cols, dw_orig);
+  sn_bwd_kernel<<<grid_for(n), 256, 0, st>>>(dw_sn, u, v, sigma, scratch, parts, rows, cols, dw_orig);
   EG_LAUNCH_CHECK("sn_bwd_kernel");
   return 0;
+}
+
+/* floats of scratch the two entry points need (per-split / per-block partial sums live there) */
+extern "C" size_t eadgan_spectral_norm_scratch_floats(int rows, int cols, int backward) {
+  if (backward) return (size_t)grid_for((int64_t)rows * cols) + 8;
+  return (size_t)rows + (size_t)((rows + 15) / 16 + 1) * (size_t)cols + 8;
 }

@@ -178,7 +178,7 @@ struct TcParams {
   int gemm_m, gemm_n;  // MODE_GEMM extents
   int n_store;         // real output channels (<= N_total; the rest is zero padding of the operand)
   int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
-  int m_tiles, n_tiles, parities;  // persistent tile space: tile = (parity * m_tiles + m_tile) * n_tiles + n_tile
+  int m_tiles, n_tiles, parities;  // persistent tile space: tile = (m_tile * parities + parity) * n_tiles + n_tile
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
 };
 
@@ -229,12 +229,62 @@ __device__ __forceinline__ void warp_col_sums(const float* v, bool valid, int la
   o2 = s2[0];
 }
 
+
+// where row `row` of sub-tile h of persistent tile `tile` lives in the output / mask tensors
+struct RowInfo {
+  bool valid, f32_out;
+  int n0, bias_base;
+  int64_t out_off, ch_stride, mask_off;
+};
+template <int BLOCK_N, int MT>
+__device__ __forceinline__ RowInfo row_info(const TcParams& P, int tile, int h, int row) {
+  RowInfo ri;
+  const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
+  const int parity = r % P.parities, m_tile = (r / P.parities) * MT + h;
+  const int py = parity >> 1, px = parity & 1;
+  const int n0 = n_tile * BLOCK_N;
+  ri.n0 = n0; ri.bias_base = n0; ri.out_off = 0; ri.ch_stride = 1; ri.mask_off = 0;
+  if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) {
+    const int m = m_tile * BLOCK_M + row;
+    ri.valid = m < P.gemm_m;
+    if (P.mode == MODE_GEMM && P.dense_C > 0) {
+      // scatter: GEMM column n = tap * C + ch  ->  padded map [m][1+ky][1+kx][ch]
+      const int tap = n0 / P.dense_C, ch0 = n0 - tap * P.dense_C;
+      ri.out_off = (((int64_t)m * 6 + 1 + (tap >> 2)) * 6 + 1 + (tap & 3)) * P.dense_C + ch0;
+      ri.mask_off = ri.out_off;
+      ri.bias_base = ch0;
+      ri.f32_out = false;
+    } else {
+      ri.out_off = (int64_t)m * P.n_store + n0;
+      ri.f32_out = true;
+    }
+  } else {
+    const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
+    const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
+    const int b = b0 + bl;
+    ri.valid = b < P.n;
+    int oy, ox;
+    if (P.mode == MODE_FPROP) { oy = y0 + yl; ox = xl; }
+    else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
+    const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
+    ri.mask_off = pad_off;
+    ri.f32_out = P.out_f32_nchw != 0;
+    if (ri.f32_out) {
+      ri.out_off = (((int64_t)b * P.n_store + n0) * P.OH + oy) * P.OW + ox;
+      ri.ch_stride = (int64_t)P.OH * P.OW;
+    } else {
+      ri.out_off = pad_off;
+    }
+  }
+  return ri;
+}
+
 // ------------------------------------------------------------------------------------
 // fprop / dgrad / gemm kernel.  PERSISTENT: grid <= number of SMs, CTA c runs tiles c, c+grid, ...
 // (n-tile fastest so concurrently running CTAs share the streamed A operand through L2).
 // ------------------------------------------------------------------------------------
 template <int BLOCK_N, int MT>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams P) {
   using C = Cfg<BLOCK_N, MT>;
@@ -259,14 +309,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
       fence_barrier_init();
     }
     __syncwarp();
     tmem_alloc(tmem_ptr, C::TMEM_COLS);
   }
   if (warp >= 2 && P.want_stats) {
-    for (int i = threadIdx.x - 64; i < 2 * P.stat_channels; i += 128) stat_acc[i] = 0.0;
+    for (int i = threadIdx.x - 64; i < 2 * P.stat_channels; i += 256) stat_acc[i] = 0.0;
   }
   tc_fence_before();
   __syncthreads();
@@ -279,7 +329,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
-        const int m_grp = r % P.m_tiles, parity = r / P.m_tiles;   // m_grp: group of MT consecutive 128-row tiles
+        // parity next-fastest: the 4 output parities of an M tile read the SAME input tile (shifted taps), so they
+        // run back to back / side by side and share it through L2 instead of re-streaming it from HBM 4 times
+        const int parity = r % P.parities, m_grp = r / P.parities;   // m_grp: group of MT consecutive 128-row tiles
         const int py = parity >> 1, px = parity & 1;
         const int n0 = n_tile * BLOCK_N;
         for (int kb = 0; kb < P.nkb; ++kb) {
@@ -349,199 +401,177 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       }
     }
   } else {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int quad = warp & 3;          // TMEM lane quadrant this warp may read
-    const int row = quad * 32 + lane;   // row of the 128-row tile
-    const int et = threadIdx.x - 64;    // 0..127
+    // ===== epilogue: TMEM -> registers -> global.  8 warps: two per TMEM lane quadrant, splitting the
+    // 32-column chunks of the tile between them (chunk ci belongs to warp-half ci & 1) =====
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int half = (warp - 2) >> 2;     // 0: warps 2..5, 1: warps 6..9
+    const int row = quad * 32 + lane;     // row of the 128-row tile
+    const int et = threadIdx.x - 64;      // 0..255
+    constexpr int NCHUNK = BLOCK_N / 32;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
-      const int m_grp = r % P.m_tiles, parity = r / P.m_tiles;
-      const int py = parity >> 1, px = parity & 1;
-      const int n0 = n_tile * BLOCK_N;
+      if (P.mask_mode) {
+        // pull the NEXT tile's mask rows into L2 now: by the time its accumulator is ready the loads below
+        // are L2 hits instead of DRAM round trips (the epilogue is latency-bound otherwise)
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {
+            const RowInfo ri = row_info<BLOCK_N, MT>(P, nt, h, row);
+            if (ri.valid) {
+              for (int l = half; l < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); l += 2)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mask + ri.mask_off + l * 64));
+            }
+          }
+        }
+      }
       const int buf = it & 1;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (half >= NCHUNK) {  // BLOCK_N = 32: the second warp of each quadrant has no columns
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      }
 #pragma unroll 1
       for (int h = 0; h < MT; ++h) {
-      const int m_tile = m_grp * MT + h;
-      int b0 = 0, y0 = 0;
-      if (P.mode == MODE_FPROP || P.mode == MODE_DGRAD) {
-        b0 = (m_tile / P.tiles_y) * P.Tb;
-        y0 = (m_tile % P.tiles_y) * P.Th;
-      }
-      bool valid;
-      int64_t out_off = 0;     // element offset of (pixel, channel n0) in the output
-      int64_t ch_stride = 1;   // element stride between channels in the output
-      int64_t mask_off = 0;
-      int bias_base = n0;      // channel index of accumulator column 0 of this tile
-      bool f32_out;
-      if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) {
-        const int m = m_tile * BLOCK_M + row;
-        valid = m < P.gemm_m;
-        if (P.mode == MODE_GEMM && P.dense_C > 0) {
-          // scatter: GEMM column n = tap * C + ch  ->  padded map [m][1+ky][1+kx][ch]
-          const int tap = n0 / P.dense_C, ch0 = n0 - tap * P.dense_C;
-          out_off = (((int64_t)m * 6 + 1 + (tap >> 2)) * 6 + 1 + (tap & 3)) * P.dense_C + ch0;
-          mask_off = out_off;
-          bias_base = ch0;
-          f32_out = false;
-        } else {
-          out_off = (int64_t)m * P.n_store + n0;
-          f32_out = true;
-        }
-      } else {
-        const int xl = row % P.Tw, yl = (row / P.Tw) % P.Th, bl = row / (P.Tw * P.Th);
-        const int b = b0 + bl;
-        valid = b < P.n;
-        int oy, ox;
-        if (P.mode == MODE_FPROP) { oy = y0 + yl; ox = xl; }
-        else { oy = 2 * (y0 + yl) + py; ox = 2 * xl + px; }
-        const int64_t pad_off = (((int64_t)b * (P.OH + 2) + oy + 1) * (P.OW + 2) + ox + 1) * P.N_total + n0;
-        mask_off = pad_off;
-        f32_out = P.out_f32_nchw != 0;
-        if (f32_out) {
-          out_off = (((int64_t)b * P.n_store + n0) * P.OH + oy) * P.OW + ox;
-          ch_stride = (int64_t)P.OH * P.OW;
-        } else {
-          out_off = pad_off;
-        }
-      }
-
-      const uint32_t acc = tmem_base + (uint32_t)(buf * C::BUF_COLS + h * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
+        const RowInfo ri = row_info<BLOCK_N, MT>(P, tile, h, row);
+        const bool valid = ri.valid, f32_out = ri.f32_out;
+        const int n0 = ri.n0, bias_base = ri.bias_base;
+        const int64_t ch_stride = ri.ch_stride;
+        const uint32_t acc = tmem_base + (uint32_t)(buf * C::BUF_COLS + h * C::ACC_COLS) + ((uint32_t)(quad * 32) << 16);
 
 #pragma unroll 1
-      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        const int n_left = P.n_store - (n0 + c0);  // real channels remaining from this column on
-        const bool live = valid && (n_left > 0 || P.dense_C > 0);
-        uint4 mv[4];
-        if (P.mask_mode && live) {  // issue the mask loads before waiting for the accumulator
-          const uint4* mp = reinterpret_cast<const uint4*>(P.mask + mask_off + c0);
+        for (int ci = half; ci < NCHUNK; ci += 2) {
+          const int c0 = ci * 32;
+          const int n_left = P.n_store - (n0 + c0);  // real channels remaining from this column on
+          const bool live = valid && (n_left > 0 || P.dense_C > 0);
+          uint4 mv[4];
+          if (P.mask_mode && live) {  // issue the mask loads before waiting for the accumulator
+            const uint4* mp = reinterpret_cast<const uint4*>(P.mask + ri.mask_off + c0);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) mv[g] = __ldg(mp + g);
-        }
-        float v[32];
-        tmem_ld32(acc + (uint32_t)c0, v);
-        if (c0 + 32 >= BLOCK_N && h == MT - 1) {
-          // every column of this accumulator is in registers: hand the TMEM buffer back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        }
-        if (P.bias) {
-          if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast loads
-            const float4* bp = reinterpret_cast<const float4*>(P.bias + bias_base + c0);
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const float4 b4 = __ldg(bp + g);
-              v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < n_left) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
+            for (int g = 0; g < 4; ++g) mv[g] = __ldg(mp + g);
           }
-        }
-        if (P.want_stats == 1) {  // BatchNorm statistics of the pre-activation output
-          float o1, o2;
-          warp_col_sums<true>(v, valid, lane, o1, o2);
-          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
-          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = o2;
-        }
-        if (live) {
-          // the activation kind is uniform for the launch: branch ONCE, outside the element loops
-          if (P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU) {
-            const float sl = P.act == EADGAN_ACT_RELU ? 0.f : P.slope;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-          } else if (P.act == EADGAN_ACT_TANH) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-          } else if (P.act == EADGAN_ACT_SIGMOID) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          float v[32];
+          tmem_ld32(acc + (uint32_t)c0, v);
+          if (ci + 2 >= NCHUNK && h == MT - 1) {
+            // all of this warp's columns are in registers: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
           }
-          if (P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU) {
-            const float sl = P.mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
+          if (P.bias) {
+            if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast loads
+              const float4* bp = reinterpret_cast<const float4*>(P.bias + bias_base + c0);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                // saved OUTPUT y > 0  <=>  pre-activation > 0; bf16 sign/zero test on the raw bits
-                const bool lo_pos = (mw[e] & 0x8000u) == 0 && (mw[e] & 0x7fffu) != 0;
-                const bool hi_pos = (mw[e] & 0x80000000u) == 0 && (mw[e] & 0x7fff0000u) != 0;
-                if (!lo_pos) v[g * 8 + e * 2 + 0] *= sl;
-                if (!hi_pos) v[g * 8 + e * 2 + 1] *= sl;
+              for (int g = 0; g < 8; ++g) {
+                const float4 b4 = __ldg(bp + g);
+                v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
               }
-            }
-          } else if (P.mask_mode) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float m_lo = __uint_as_float(mw[e] << 16), m_hi = __uint_as_float(mw[e] & 0xffff0000u);
-                v[g * 8 + e * 2 + 0] *= eg_act_grad(m_lo, P.mask_mode, P.slope);
-                v[g * 8 + e * 2 + 1] *= eg_act_grad(m_hi, P.mask_mode, P.slope);
-              }
-            }
-          }
-        }
-        if (P.want_stats == 2) {  // per-channel sums of the FINAL value (bias gradient of the layer below)
-          float o1, o2;
-          warp_col_sums<false>(v, live, lane, o1, o2);
-          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
-          stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = 0.f;
-        }
-        if (live) {
-          if (f32_out) {
-            float* op = reinterpret_cast<float*>(P.out) + out_off + (int64_t)c0 * ch_stride;
-            if (ch_stride == 1 && n_left >= 32 && (P.n_store & 3) == 0) {
-#pragma unroll
-              for (int g = 0; g < 8; ++g)
-                *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
+                if (j < n_left) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
             }
-          } else {
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + out_off + c0;
+          }
+          if (P.want_stats == 1) {  // BatchNorm statistics of the pre-activation output
+            float o1, o2;
+            warp_col_sums<true>(v, valid, lane, o1, o2);
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = o2;
+          }
+          if (live) {
+            // the activation kind is uniform for the launch: branch ONCE, outside the element loops
+            if (P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU) {
+              const float sl = P.act == EADGAN_ACT_RELU ? 0.f : P.slope;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              uint32_t pk[4];
+              for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+            } else if (P.act == EADGAN_ACT_TANH) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+              for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+            } else if (P.act == EADGAN_ACT_SIGMOID) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+            }
+            if (P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU) {
+              const float sl = P.mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  // saved OUTPUT y > 0  <=>  pre-activation > 0; bf16 sign/zero test on the raw bits
+                  const bool lo_pos = (mw[e] & 0x8000u) == 0 && (mw[e] & 0x7fffu) != 0;
+                  const bool hi_pos = (mw[e] & 0x80000000u) == 0 && (mw[e] & 0x7fff0000u) != 0;
+                  if (!lo_pos) v[g * 8 + e * 2 + 0] *= sl;
+                  if (!hi_pos) v[g * 8 + e * 2 + 1] *= sl;
+                }
               }
-              *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            } else if (P.mask_mode) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                const uint32_t mw[4] = {mv[g].x, mv[g].y, mv[g].z, mv[g].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float m_lo = __uint_as_float(mw[e] << 16), m_hi = __uint_as_float(mw[e] & 0xffff0000u);
+                  v[g * 8 + e * 2 + 0] *= eg_act_grad(m_lo, P.mask_mode, P.slope);
+                  v[g * 8 + e * 2 + 1] *= eg_act_grad(m_hi, P.mask_mode, P.slope);
+                }
+              }
+            }
+          }
+          if (P.want_stats == 2) {  // per-channel sums of the FINAL value (bias gradient of the layer below)
+            float o1, o2;
+            warp_col_sums<false>(v, live, lane, o1, o2);
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = 0.f;
+          }
+          if (live) {
+            if (f32_out) {
+              float* op = reinterpret_cast<float*>(P.out) + ri.out_off + (int64_t)c0 * ch_stride;
+              if (ch_stride == 1 && n_left >= 32 && (P.n_store & 3) == 0) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                  *reinterpret_cast<float4*>(op + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
+              }
+            } else {
+              __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ri.out_off + c0;
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint32_t pk[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  __nv_bfloat162 h2 = __floats2bfloat162_rn(v[g * 8 + e * 2], v[g * 8 + e * 2 + 1]);
+                  pk[e] = *reinterpret_cast<uint32_t*>(&h2);
+                }
+                *reinterpret_cast<uint4*>(op + g * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              }
             }
           }
         }
-      }
-      if (P.want_stats) {
-        // fold the four warps' partials of this tile into the CTA's running per-channel totals
-        // (thread et owns channels bias_base + et, + et + 128: no conflicts, no atomics)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int ch = et; ch < BLOCK_N; ch += 128) {
-          const int gch = bias_base + ch;
-          if (gch < P.stat_channels) {
-            float a = 0.f, b2 = 0.f;
+        if (P.want_stats) {
+          // fold the four quadrants' partials of this sub-tile into the CTA's running per-channel totals
+          // (thread et owns channel bias_base + et [+ 256 ...]: no conflicts, no atomics)
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          for (int ch = et; ch < BLOCK_N; ch += 256) {
+            const int gch = bias_base + ch;
+            if (gch < P.stat_channels) {
+              float a = 0.f, b2 = 0.f;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) { a += stat_part[(w * BLOCK_N + ch) * 2]; b2 += stat_part[(w * BLOCK_N + ch) * 2 + 1]; }
-            stat_acc[gch * 2 + 0] += (double)a;
-            stat_acc[gch * 2 + 1] += (double)b2;
+              for (int w = 0; w < 4; ++w) { a += stat_part[(w * BLOCK_N + ch) * 2]; b2 += stat_part[(w * BLOCK_N + ch) * 2 + 1]; }
+              stat_acc[gch * 2 + 0] += (double)a;
+              stat_acc[gch * 2 + 1] += (double)b2;
+            }
           }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
       }  // sub-tile h
     }
     if (P.want_stats) {
       // one flush per CTA: 2 fp64 atomics per channel
-      for (int ch = et; ch < P.stat_channels; ch += 128) {
+      for (int ch = et; ch < P.stat_channels; ch += 256) {
         const double a = stat_acc[ch * 2], b2 = stat_acc[ch * 2 + 1];
         if (a != 0.0 || b2 != 0.0) {
           atomicAdd(&P.stats[ch], a);
@@ -880,7 +910,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P,
   const int sms = eg_sm_count();
   const int waves = (total + sms - 1) / sms;
   const int grid = (total + waves - 1) / waves;
-  tc_conv_kernel<BN, MT><<<grid, 192, Cfg<BN, MT>::SMEM, st>>>(ma, mb, P);
+  tc_conv_kernel<BN, MT><<<grid, 320, Cfg<BN, MT>::SMEM, st>>>(ma, mb, P);
   EG_LAUNCH_CHECK("tc_conv_kernel");
   return 0;
 }

@@ -343,7 +343,8 @@ class _SpectralNormFn(torch.autograd.Function):
         cols = w.numel() // rows
         sigma = torch.empty(1, device=w.device, dtype=torch.float32)
         w_sn = torch.empty_like(w)
-        scratch = torch.empty(rows + cols + 8, device=w.device, dtype=torch.float32)
+        scratch = torch.empty(L.lib().eadgan_spectral_norm_scratch_floats(rows, cols, 0), device=w.device,
+                              dtype=torch.float32)
         call("eadgan_spectral_norm_fwd", ptr(w), rows, cols, ptr(u), ptr(v), 1 if do_power_iter else 0,
              float(eps), ptr(sigma), ptr(w_sn), ptr(scratch), stream())
         ctx.mark_non_differentiable(sigma)
@@ -359,7 +360,8 @@ class _SpectralNormFn(torch.autograd.Function):
         rows = w.shape[0]
         cols = w.numel() // rows
         dw = torch.empty_like(w)
-        scratch = torch.empty(8, device=w.device, dtype=torch.float32)
+        scratch = torch.empty(L.lib().eadgan_spectral_norm_scratch_floats(rows, cols, 1), device=w.device,
+                              dtype=torch.float32)
         call("eadgan_spectral_norm_bwd", ptr(dw_sn), ptr(w), ptr(u), ptr(v), ptr(sigma), rows, cols, ptr(dw),
              ptr(scratch), stream())
         return dw, None, None, None, None

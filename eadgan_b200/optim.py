@@ -27,6 +27,27 @@ class Adam(torch.optim.Optimizer):
             raise ValueError("Invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
         self._dp = None  # set by eadgan_b200.parallel.attach()
+        self._step_dev = None       # device int64 step counter (CUDA-graph capture, eadgan_b200.graph)
+        self._captured = None       # parameters stepped by the captured step() (their python "step" mirrors)
+
+    # ---- CUDA-graph support (eadgan_b200.graph.GraphedStep) -----------------------------------------
+    def prepare_capture(self):
+        """call OUTSIDE capture, after at least one eager step: loads the device step counter with the
+        current step count.  Inside capture, step() advances and reads it on the device."""
+        steps = {st["step"] for st in self.state.values() if "step" in st}
+        if len(steps) != 1:
+            raise RuntimeError("eadgan_b200.Adam: graph capture needs one common step count over the parameters "
+                               f"that receive gradients (found {sorted(steps)}); run an eager step first")
+        dev = next(iter(self.state)).device
+        if self._step_dev is None:
+            self._step_dev = torch.zeros(1, device=dev, dtype=torch.int64)
+        self._step_dev.fill_(steps.pop())
+        self._captured = None
+
+    def on_replay(self):
+        """python-side mirror of the device counter: one more step has been (re)played"""
+        for p in self._captured or ():
+            self.state[p]["step"] += 1
 
     def zero_grad(self, set_to_none: bool = True):
         super().zero_grad(set_to_none=set_to_none)
@@ -41,6 +62,12 @@ class Adam(torch.optim.Optimizer):
                 loss = closure()
         reduced = self._dp.reduce(self) if self._dp is not None else None  # {param: reduced grad}
         gscale = 1.0 if self._dp is None else 1.0 / self._dp.world_size
+        capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        if capturing:
+            if self._step_dev is None:
+                raise RuntimeError("eadgan_b200.Adam: call prepare_capture() before capturing step() in a CUDA graph")
+            call("eadgan_adam_advance", C.c_void_p(self._step_dev.data_ptr()), stream())
+            self._captured = []
         for group in self.param_groups:
             beta1, beta2 = group["betas"]
             ps, gs, ms, vs = [], [], [], []
@@ -59,9 +86,13 @@ class Adam(torch.optim.Optimizer):
                     st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                     st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
                 st["step"] += 1
+                if capturing:
+                    self._captured.append(p)
                 if t is None:
                     t = st["step"]
                 elif t != st["step"]:
+                    if capturing:
+                        raise RuntimeError("eadgan_b200.Adam: parameters with different step counts cannot be captured")
                     self._launch(ps, gs, ms, vs, group, t, gscale)
                     ps, gs, ms, vs = [], [], [], []
                     t = st["step"]
@@ -70,11 +101,11 @@ class Adam(torch.optim.Optimizer):
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
             if ps:
-                self._launch(ps, gs, ms, vs, group, t, gscale)
+                self._launch(ps, gs, ms, vs, group, t, gscale, self._step_dev if capturing else None)
         return loss
 
     @staticmethod
-    def _launch(ps, gs, ms, vs, group, t, gscale):
+    def _launch(ps, gs, ms, vs, group, t, gscale, step_dev=None):
         beta1, beta2 = group["betas"]
         bc1 = 1.0 - beta1 ** t
         bc2 = 1.0 - beta2 ** t
@@ -93,5 +124,9 @@ class Adam(torch.optim.Optimizer):
                 A.v[j] = vs[i].data_ptr()
                 A.numel[j] = ps[i].numel()
             A.count = len(chunk)
-            call("eadgan_adam_step", C.byref(A), float(beta1), float(beta2), float(group["eps"]),
-                 float(step_size), float(bc2_sqrt), float(gscale), st)
+            if step_dev is not None:
+                call("eadgan_adam_step_dev", C.byref(A), float(beta1), float(beta2), float(group["eps"]),
+                     float(group["lr"]), C.c_void_p(step_dev.data_ptr()), float(gscale), st)
+            else:
+                call("eadgan_adam_step", C.byref(A), float(beta1), float(beta2), float(group["eps"]),
+                     float(step_size), float(bc2_sqrt), float(gscale), st)

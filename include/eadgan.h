@@ -237,7 +237,9 @@ int eadgan_upsample2x_bwd(const float* dy, float* dx, int nc, int h, int w, void
 /* dSprites/rp.py:95-109,165-183, MNIST/EAD-GAN_rpqmnxy.py:107,124,143,161-163 */
 /* ------------------------------------------------------------------------- */
 /* one power iteration in place on u[rows], v[cols] (skipped when do_power_iter == 0),
- * sigma = u^T W v, w_sn = W / sigma.  scratch: >= (rows + cols + 8) floats. */
+ * sigma = u^T W v, w_sn = W / sigma.  scratch: eadgan_spectral_norm_scratch_floats(rows, cols, 0) floats
+ * (split partial sums are kept there and added in a fixed order: the result is run-to-run deterministic). */
+size_t eadgan_spectral_norm_scratch_floats(int rows, int cols, int backward);
 int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols, float* u, float* v,
                              int do_power_iter, float eps, float* sigma, float* w_sn,
                              float* scratch, void* stream);
@@ -288,6 +290,12 @@ typedef struct {
  * host exactly as torch does; grad_scale multiplies g on load (1/world_size for DP sums). */
 int eadgan_adam_step(const eadgan_adam_tensors* t, double beta1, double beta2, double eps,
                      double step_size, double bc2_sqrt, float grad_scale, void* stream);
+/* CUDA-graph form: the step count t is a DEVICE int64 (advanced by eadgan_adam_advance inside the captured
+ * step), and lr/(1-beta1^t), sqrt(1-beta2^t) are formed on the device in double -- so a captured
+ * optimiser step stays correct across replays (the host form bakes t into the kernel arguments). */
+int eadgan_adam_step_dev(const eadgan_adam_tensors* t, double beta1, double beta2, double eps, double lr,
+                         const int64_t* step_dev, float grad_scale, void* stream);
+int eadgan_adam_advance(int64_t* step_dev, void* stream);
 
 /* fill / scale helpers used by the host layer (buffer zeroing stays on our stream) */
 int eadgan_fill_f32(float* p, int64_t numel, float value, void* stream);

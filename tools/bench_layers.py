@@ -59,3 +59,7 @@ for c, h, k in LAYERS:
             continue
         ms = timeit(fn)
         print(f"B={B} c={c:4d} h={h:3d} k={k:4d} {name:18s} {ms:8.4f} ms  {flops / ms / 1e9:8.1f} TF/s", flush=True)
+
+# calibration of this box: cuBLAS bf16 8192^3 (the MEASURED_PEAKS.json denominator), same process
+a = torch.randn(8192, 8192, device=dev).bfloat16(); b = torch.randn(8192, 8192, device=dev).bfloat16()
+print(f"calibration: torch.matmul bf16 8192^3 {2.0 * 8192 ** 3 / timeit(lambda: torch.matmul(a, b)) / 1e9:8.1f} TF/s")
