@@ -193,11 +193,16 @@ def main():
     sampler = ClockSampler(local) if rank == 0 else None
     k0 = _lib.lib().eadgan_kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    window = os.environ.get("EADGAN_PROFILE_WINDOW") == "1"   # ncu --profile-from-start off: only the timed steps
+    if window:
+        torch.cuda.profiler.start()
     e0.record()
     for i in range(args.steps):
         step(*resident[i % R])
     e1.record()
     torch.cuda.synchronize()
+    if window:
+        torch.cuda.profiler.stop()
     launches = _lib.lib().eadgan_kernel_launches() - k0
     if use_graph:
         launches = step.kernels_per_replay * args.steps   # replays do not pass through the C-ABI launch counter

@@ -60,8 +60,8 @@ _PROTOS = {
     "eadgan_tc_dense_gather": [_P, _P, _P, _P, _I, _I, _I, _P],
     "eadgan_tc_dense_scatter": [_P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_wgrad": [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P],
-    "eadgan_tc_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
-    "eadgan_tc_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P],
+    "eadgan_tc_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "eadgan_tc_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "eadgan_tc_wgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, C.c_size_t, _P],
     "eadgan_tc_gemm": [_P, _P, _P, _I, _I, _I, _P],
     "eadgan_copy4": [_T4, _T4, _I, _I, _I, _I, _P],
@@ -105,6 +105,15 @@ _SPECIAL = {
     "eadgan_spectral_norm_scratch_floats": ([_I, _I, _I], C.c_size_t),
 }
 EXPORTED = sorted(list(_PROTOS) + list(_SPECIAL))
+
+weights_epoch = 0  # bumped whenever parameters may have changed behind torch's version counters (Adam.step,
+                   # load_state_dict): invalidates the packed-weight cache of eadgan_b200.tc
+
+
+def bump_weights_epoch():
+    global weights_epoch
+    weights_epoch += 1
+
 
 _lib = None
 launches = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from it)

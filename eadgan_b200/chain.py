@@ -104,15 +104,26 @@ def try_run(seq, x):
         return None
     if any(st.bn is not None and not st.bn.training for st in stages):
         return None  # eval-mode BN: per-op path
-    params = []
+    params, srcs = [], []
     for st in stages:
+        st.conv.__dict__.pop("_eadgan_sn_src", None)
         for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
             hook(st.conv, (x,))
-        params += [st.conv.weight, st.conv.bias]
+        w = st.conv.weight
+        # what the tensor-core path packs: the parameter itself (cached until it changes), with sigma applied
+        # in the kernel epilogue for spectral-normalised layers; any other weight tensor is packed as is
+        sn = st.conv.__dict__.get("_eadgan_sn_src")
+        if sn is not None and sn[2] is w and isinstance(sn[0], torch.nn.Parameter):
+            srcs.append((sn[0], sn[1]))
+        elif isinstance(w, torch.nn.Parameter):
+            srcs.append((w, None))
+        else:
+            srcs.append(None)
+        params += [w, st.conv.bias]
         if st.bn is not None:
             st.bn.num_batches_tracked.add_(1)
             params += [st.bn.weight, st.bn.bias]
-    return _ChainFn.apply(x, stages, *params)
+    return _ChainFn.apply(x, stages, srcs, *params)
 
 
 # ------------------------------------------------------------------------------------------
@@ -206,7 +217,7 @@ def _r64(v):
 
 class _ChainFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, stages, *params):
+    def forward(ctx, x, stages, srcs, *params):
         st_ = stream()
         dev = x.device
         cur = _Buf(x.contiguous(), "ext")
@@ -229,6 +240,14 @@ class _ChainFn(torch.autograd.Function):
             wc = w.contiguous()
             impl = _impl(st, d, last)
             rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl}
+            src = srcs[si]
+
+            def packed(direction, ca, _src=src, _wc=wc):
+                """(bf16 GEMM operand, sigma) of this stage's weight for `direction`"""
+                if _src is not None and tuple(_src[0].shape[2:]) == (4, 4):
+                    return tc.pack_w_cached(_src[0], direction, ca), _src[1]
+                return tc.pack_w(_wc, None, direction, ca), None
+            rec["packed"] = packed
             if impl == "dense_T":      # 1x1 -> 4x4 ConvTranspose: batch GEMM, scatter epilogue
                 a = tc.pad_rows(cur.t.reshape(d.n, d.k), _r64(d.k))
                 out = _Buf(tc.dense_scatter(a, tc.dense_pack(wc, _r64(d.k), False), b, d.c), "pad")
@@ -242,13 +261,14 @@ class _ChainFn(torch.autograd.Function):
                 ca = _calloc(d)
                 if st.kind == "conv":
                     inp = _Buf(cur.t if cur.fmt == "pad" else tc.to_padded(cur.t, ca), "pad")
-                    wpk = tc.pack_w(wc, None, "fprop", ca)
-                    out_t = tc.fprop(inp.t, wpk, b, cout, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats)
+                    wpk, sg = packed("fprop", ca)
+                    out_t = tc.fprop(inp.t, wpk, b, cout, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats,
+                                     sigma=sg)
                 else:
                     inp = _Buf(cur.padded(), "pad")
-                    wpk = tc.pack_w(wc, None, "dgrad", ca)
+                    wpk, sg = packed("dgrad", ca)
                     out_t = tc.dgrad(inp.t, wpk, b, ca, epi_act[0], epi_act[1], out_f32_nchw=last, stats=stats,
-                                     c_real=d.c if ca != d.c else 0)
+                                     c_real=d.c if ca != d.c else 0, sigma=sg)
                 out = _Buf(out_t, "ext" if last else "pad")
             else:
                 inp = cur
@@ -388,16 +408,16 @@ class _ChainFn(torch.autograd.Function):
                     if tc_dx and ca != d.c and st.kind == "conv" and si > 0:
                         tc_dx = False  # zero-padded result channels need the fp32 NCHW epilogue (si == 0)
                     if tc_dx:
-                        wpk = tc.pack_w(sv["w"], None, direction, ca)
+                        wpk, sg = sv["packed"](direction, ca)
                         if st.kind == "conv":
                             dx_t = tc.dgrad(dz.padded(), wpk, None, ca, mask=sv["inp"].t if fuse else None,
                                             mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0),
-                                            c_real=d.c if ca != d.c else 0, stats=sums_buf, stats_mode=2)
+                                            c_real=d.c if ca != d.c else 0, stats=sums_buf, stats_mode=2, sigma=sg)
                         else:
                             dzp = dz.t if dz.fmt == "pad" else tc.to_padded(dz.t, ca)
                             dx_t = tc.fprop(dzp, wpk, None, in_shape[1], mask=sv["inp"].t if fuse else None,
                                             mask_mode=mask_act, slope=mask_slope, out_f32_nchw=(si == 0),
-                                            stats=sums_buf, stats_mode=2)
+                                            stats=sums_buf, stats_mode=2, sigma=sg)
                         dx = _Buf(dx_t, "ext" if si == 0 else "pad")
                         sums_used = want_sums
             if need_dx and dx is None:   # generic SIMT input gradient on the same buffers
@@ -422,4 +442,4 @@ class _ChainFn(torch.autograd.Function):
             grads = stage_grads + grads
         dx0 = g.t if ctx.needs_input_grad[0] else None
         ctx.saved = None
-        return (dx0, None, *grads)
+        return (dx0, None, None, *grads)

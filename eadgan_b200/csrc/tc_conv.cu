@@ -180,6 +180,8 @@ struct TcParams {
   int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
   int m_tiles, n_tiles, parities;  // persistent tile space: tile = (m_tile * parities + parity) * n_tiles + n_tile
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
+  const float* sigma;  // spectral-norm sigma (device scalar) or NULL: accumulators are multiplied by 1/sigma, so the
+                       // packed bf16 operand can be the UN-normalised weight_orig (cached across forwards)
 };
 
 constexpr int BLOCK_M = 128;
@@ -408,6 +410,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int row = quad * 32 + lane;     // row of the 128-row tile
     const int et = threadIdx.x - 64;      // 0..255
     constexpr int NCHUNK = BLOCK_N / 32;
+    const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       if (P.mask_mode) {
@@ -457,6 +460,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+          if (P.sigma) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= inv_sigma;
           }
           if (P.bias) {
             if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast loads
@@ -990,7 +997,7 @@ extern "C" int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k,
 }
 
 extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const void* w_packed, const float* bias,
-                               void* y, const void* mask, double* stats, void* stream) {
+                               void* y, const void* mask, double* stats, const float* sigma, void* stream) {
   if (int e = check_tc(d, "tc_fprop")) return e;
   EG_REQUIRE(x_pad && w_packed && y, EADGAN_ERR_INVALID, "tc_fprop: NULL pointer");
   const int p = d->h / 2, q = d->w / 2;
@@ -1005,7 +1012,7 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = d->c; P.qblocks = 2 * d->c / 64; P.nkb = 8 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
-  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k; P.stat_channels = d->k;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k; P.stat_channels = d->k; P.sigma = sigma;
   EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_fprop: mask_mode without mask");
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_fprop: want_stats without stats");
   CUtensorMap ma, mb;
@@ -1015,7 +1022,7 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
 }
 
 extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed, const float* bias,
-                               void* dx, const void* mask, double* stats, void* stream) {
+                               void* dx, const void* mask, double* stats, const float* sigma, void* stream) {
   if (int e = check_tc(d, "tc_dgrad")) return e;
   EG_REQUIRE(dy_pad && w_packed && dx, EADGAN_ERR_INVALID, "tc_dgrad: NULL pointer");
   const int p = d->h / 2, q = d->w / 2;
@@ -1030,7 +1037,7 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = d->k / 64; P.nkb = 4 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
-  P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.sigma = sigma;
   P.n_store = (d->c_real > 0 && d->c_real < d->c) ? d->c_real : d->c;
   P.stat_channels = P.n_store;
   EG_REQUIRE(P.n_store == d->c || d->out_f32_nchw, EADGAN_ERR_UNSUPPORTED,

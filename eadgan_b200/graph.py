@@ -15,7 +15,7 @@ from __future__ import annotations
 
 import torch
 
-from . import _lib
+from . import _lib, tc
 
 
 class GraphedStep:
@@ -35,8 +35,12 @@ class GraphedStep:
             o.prepare_capture()
         self.graph = torch.cuda.CUDAGraph()
         k0 = _lib.lib().eadgan_kernel_launches()
+        # packed-weight cache: a hit during capture would leave the pack kernel OUT of the graph (stale weights on
+        # replay), and an entry filled during capture holds nothing until the first replay -> clear on both sides
+        tc.invalidate_caches()
         with torch.cuda.graph(self.graph):
             self.static_out = step(*self.static_in)
+        tc.invalidate_caches()
         self.kernels_per_replay = int(_lib.lib().eadgan_kernel_launches() - k0)
         self._first = True
 
@@ -50,4 +54,5 @@ class GraphedStep:
             for o in self.opts:
                 o.on_replay()
         self.graph.replay()
+        _lib.bump_weights_epoch()        # the replay ran Adam steps: eager code must re-pack afterwards
         return self.static_out

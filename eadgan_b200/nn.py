@@ -47,7 +47,16 @@ def _single(v, what):
     return int(v)
 
 
-class Conv2d(_TorchConv2d):
+class _InvalidateOnLoad:
+    """mix-in: loading a state_dict rewrites parameters in place -> drop packed-weight caches"""
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        from . import _lib
+        _lib.bump_weights_epoch()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+
+class Conv2d(_InvalidateOnLoad, _TorchConv2d):
     def forward(self, x, act=(ACT_NONE, 0.0)):
         if self.groups != 1 or _single(self.dilation, "dilation") != 1 or self.padding_mode != "zeros":
             raise RuntimeError("eadgan_b200.Conv2d: groups/dilation/padding_mode variants are unsupported")
@@ -55,7 +64,7 @@ class Conv2d(_TorchConv2d):
                          _single(self.padding, "padding"), act[0], act[1])
 
 
-class ConvTranspose2d(_TorchConvTranspose2d):
+class ConvTranspose2d(_InvalidateOnLoad, _TorchConvTranspose2d):
     def forward(self, x, output_size=None, act=(ACT_NONE, 0.0)):
         if (self.groups != 1 or _single(self.dilation, "dilation") != 1 or output_size is not None
                 or _single(self.output_padding, "output_padding") != 0):
@@ -215,6 +224,9 @@ class SpectralNorm(_tsn.SpectralNorm):
             raise RuntimeError("eadgan_b200.spectral_norm: n_power_iterations must be 1")
         w_sn, sigma = Fn.spectral_norm_weight(weight, u, v, do_power_iteration, self.eps)
         module._eadgan_sigma = sigma
+        # (weight_orig, sigma, the tensor about to become module.weight): lets the bf16 chain pack weight_orig
+        # once per optimiser step and apply 1/sigma in the conv epilogue (eadgan_b200.chain.try_run)
+        module.__dict__["_eadgan_sn_src"] = (weight, sigma, w_sn)
         return w_sn
 
 

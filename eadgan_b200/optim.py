@@ -102,6 +102,7 @@ class Adam(torch.optim.Optimizer):
                 vs.append(st["exp_avg_sq"])
             if ps:
                 self._launch(ps, gs, ms, vs, group, t, gscale, self._step_dev if capturing else None)
+        L.bump_weights_epoch()   # parameters changed through raw pointers: packed-weight caches are stale
         return loss
 
     @staticmethod

@@ -3,6 +3,7 @@ repacking and thin wrappers over the eadgan_tc_* entry points (include/eadgan.h)
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 
 import torch
 
@@ -10,14 +11,37 @@ from . import _lib as L
 from ._lib import ACT_NONE, call, ptr, stream, t4
 
 
-def alloc_padded(n, h, w, c, device, zero_interior=False):
-    """[n, h+2, w+2, c] bf16 with a zero halo.  The interior is left uninitialised unless
-    ``zero_interior`` (every producing kernel overwrites it completely); only the halo is cleared."""
-    if zero_interior or c % 8 != 0:
-        return torch.zeros((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
-    xp = torch.empty((n, h + 2, w + 2, c), device=device, dtype=torch.bfloat16)
-    call("eadgan_zero_halo", ptr(xp), n, h, w, c, stream())
-    return xp
+# Pool of halo-padded buffers.  A buffer's halo (and, for channel-padded image buffers, its padding channels)
+# is zeroed ONCE, when the buffer is first created; after that only interiors are ever written, so a recycled
+# buffer needs no clearing at all.  Buffers are recycled per (shape, real-channel count, device) when the
+# tensor object handed out dies (the chain executor always holds the padded tensor itself, views are
+# temporaries); reuse is stream-ordered exactly like the caching allocator's.
+_pool = {}
+_pool_enabled = True
+
+
+def _recycle(key, base):
+    _pool.setdefault(key, []).append(base)
+
+
+def alloc_padded(n, h, w, c, device, zero_interior=False, c_real=None):
+    """[n, h+2, w+2, c] bf16 with a zero halo.  The interior is NOT initialised (every producing kernel
+    overwrites it completely) unless ``zero_interior``.  ``c_real`` < c: channels >= c_real are guaranteed zero
+    (the producing copy writes only the first c_real)."""
+    shape = (n, h + 2, w + 2, c)
+    if zero_interior or not _pool_enabled:
+        return torch.zeros(shape, device=device, dtype=torch.bfloat16)
+    key = (shape, c_real or c, str(device))
+    free = _pool.get(key)
+    base = free.pop() if free else torch.zeros(shape, device=device, dtype=torch.bfloat16)
+    t = base.view(shape)
+    weakref.finalize(t, _recycle, key, base)
+    return t
+
+
+def clear_pool():
+    """drop every pooled buffer (frees the memory back to torch's allocator)"""
+    _pool.clear()
 
 
 def interior(xp):
@@ -29,7 +53,7 @@ def interior(xp):
 def to_padded(x, c_alloc=None):
     """fp32/bf16 NCHW tensor -> padded NHWC bf16 (copy4 kernel); channels zero-padded to c_alloc."""
     n, c, h, w = x.shape
-    xp = alloc_padded(n, h, w, c_alloc or c, x.device, zero_interior=bool(c_alloc) and c_alloc != c)
+    xp = alloc_padded(n, h, w, c_alloc or c, x.device, c_real=c)
     src, dst = t4(x), t4(interior(xp)[:, :c])
     call("eadgan_copy4", C.byref(src), C.byref(dst), n, c, h, w, stream())
     return xp
@@ -64,12 +88,38 @@ def pack_w(w, sigma=None, direction="fprop", c_alloc=None):
     return out
 
 
+_pack_cache = {}
+
+
+def pack_w_cached(param, direction="fprop", c_alloc=None):
+    """pack_w of a PARAMETER object (a G weight, or the weight_orig of a spectral-normalised layer), cached until
+    the parameter changes: torch's version counter catches in-place torch ops (load_state_dict, stock
+    optimisers), _lib.weights_epoch catches our fused Adam (which updates through raw pointers).  Entries are
+    tied to the parameter OBJECT (weak reference), never to an address that a later tensor could reuse.  Code
+    that rewrites a parameter through ``.data`` must call eadgan_b200.invalidate_caches()."""
+    key = (id(param), direction, c_alloc)
+    token = (param._version, param.data_ptr(), L.weights_epoch)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0]() is param and hit[1] == token:
+        return hit[2]
+    out = pack_w(param.detach(), None, direction, c_alloc)
+    if hit is None or hit[0]() is not param:
+        weakref.finalize(param, _pack_cache.pop, key, None)
+    _pack_cache[key] = (weakref.ref(param), token, out)
+    return out
+
+
+def invalidate_caches():
+    _pack_cache.clear()
+    L.bump_weights_epoch()
+
+
 def _desc(n, c, h, w, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, want_stats=False, mask_mode=0, c_real=0):
     return L.TcDesc(n, c, h, w, k, act, float(slope), int(out_f32_nchw), int(want_stats), int(c_real), int(mask_mode))
 
 
 def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
-          out=None, stats_mode=1):
+          out=None, stats_mode=1, sigma=None):
     """big map xp [n,h+2,w+2,c] -> small map [n,p+2,q+2,k] (or fp32 NCHW [n,k,p,q])."""
     n, hp, wp, c = xp.shape
     h, w = hp - 2, wp - 2
@@ -77,12 +127,13 @@ def fprop(xp, wpk, bias, k, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=No
     if out is None:
         out = (torch.empty((n, k, h // 2, w // 2), device=xp.device, dtype=torch.float32) if out_f32_nchw
                else alloc_padded(n, h // 2, w // 2, k, xp.device))
-    call("eadgan_tc_fprop", C.byref(d), ptr(xp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), stream())
+    call("eadgan_tc_fprop", C.byref(d), ptr(xp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), ptr(sigma),
+         stream())
     return out
 
 
 def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=None, mask_mode=0, stats=None,
-          out=None, c_real=0, stats_mode=1):
+          out=None, c_real=0, stats_mode=1, sigma=None):
     """small map yp [n,p+2,q+2,k] -> big map [n,2p+2,2q+2,c] (or fp32 NCHW [n,c_real or c,2p,2q])."""
     n, pp, qp, k = yp.shape
     h, w = 2 * (pp - 2), 2 * (qp - 2)
@@ -90,7 +141,8 @@ def dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, out_f32_nchw=False, mask=No
     if out is None:
         out = (torch.empty((n, c_real or c, h, w), device=yp.device, dtype=torch.float32) if out_f32_nchw
                else alloc_padded(n, h, w, c, yp.device))
-    call("eadgan_tc_dgrad", C.byref(d), ptr(yp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), stream())
+    call("eadgan_tc_dgrad", C.byref(d), ptr(yp), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), ptr(sigma),
+         stream())
     return out
 
 

@@ -136,10 +136,15 @@ int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k, int c_real
 int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k, int c_real, int c,
                            void* w_packed, void* stream);
 size_t eadgan_tc_workspace_bytes(const eadgan_tc_desc* d, int direction);
+/* sigma: NULL, or a device scalar -- the accumulators are multiplied by 1/sigma before bias/activation, i.e.
+ * the layer computed is conv(x, W / sigma) with W the packed (un-normalised) operand.  This lets the bf16 pack
+ * of a spectral-normalised weight_orig be cached across the forwards of a phase (sigma changes per forward). */
 int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const void* w_packed,
-                    const float* bias, void* y, const void* mask, double* stats, void* stream);
+                    const float* bias, void* y, const void* mask, double* stats, const float* sigma,
+                    void* stream);
 int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed,
-                    const float* bias, void* dx, const void* mask, double* stats, void* stream);
+                    const float* bias, void* dx, const void* mask, double* stats, const float* sigma,
+                    void* stream);
 /* dw[k,c,4,4] fp32 = sum dy (x) patch(x); workspace holds split partial sums */
 int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const void* dy_pad, float* dw,
                     void* workspace, size_t ws_bytes, void* stream);
