@@ -71,3 +71,45 @@ def stn(img, theta23, padding_mode="border"):
     """transformation_2D.stn (celebA/EAD-GAN_celebA.py:149-153); stock torch op ("next" row f2)."""
     grid = TF.affine_grid(theta23, list(img.shape), align_corners=False)
     return TF.grid_sample(img, grid, padding_mode=padding_mode, align_corners=False)
+
+
+# ---- dSprites (dSprites/utils_pxy.py, dSprites/utils_rp.py) -----------------------------------------------
+def dsprites_align_inverse(code3):
+    """inverse(get_matrix_pxy_align(code))[:, 0:2]  (dSprites/utils_pxy.py:69-87, rp.py:374-377): the align
+    matrix is a pure translation by (0.1*c1, 0.1*c2) -- the zoom entry c0 is NOT used -- so its inverse is the
+    opposite translation."""
+    one, zero = torch.ones_like(code3[:, 0]), torch.zeros_like(code3[:, 0])
+    return torch.stack((torch.stack((one, zero, -(code3[:, 1] * 0.1)), dim=1),
+                        torch.stack((zero, one, -(code3[:, 2] * 0.1)), dim=1)), dim=1)
+
+
+def _rpt_parts(code4):
+    """(a, b, c, d, tx, ty) of R(theta) diag(p, p, 1) T(x, y)  (dSprites/utils_rp.py:38-59 == :94-115)."""
+    theta, p = code4[:, 0] * (math.pi / 9), code4[:, 1] * 0.2 + 1
+    x, y = code4[:, 2] * 0.1, code4[:, 3] * 0.1
+    c, s = torch.cos(theta), torch.sin(theta)
+    a, b, cc, d = c * p, -s * p, s * p, c * p
+    return a, b, cc, d, a * x + b * y, cc * x + d * y
+
+
+def dsprites_matrix23(code4):
+    a, b, c, d, tx, ty = _rpt_parts(code4[:, :4])
+    return torch.stack((torch.stack((a, b, tx), dim=1), torch.stack((c, d, ty), dim=1)), dim=1)
+
+
+def dsprites_relative_code(real_code, trans_code):
+    """affine_regularzier of dSprites/utils_rp.py:117-147, closed-form inverse (no host round trip)."""
+    a1, b1, c1, d1, x1, y1 = _rpt_parts(real_code[:, :4])
+    a2, b2, c2, d2, x2, y2 = _rpt_parts(trans_code[:, :4])
+    det = a1 * d1 - b1 * c1
+    ia, ib, ic, id_ = d1 / det, -b1 / det, -c1 / det, a1 / det
+    itx, ity = -(ia * x1 + ib * y1), -(ic * x1 + id_ * y1)
+    r00, r01 = a2 * ia + b2 * ic, a2 * ib + b2 * id_
+    r10, r11 = c2 * ia + d2 * ic, c2 * ib + d2 * id_
+    r02, r12 = a2 * itx + b2 * ity + x2, c2 * itx + d2 * ity + y2
+    th = torch.atan((r10 - r01) / (r00 + r11))
+    ct, st = torch.cos(th), torch.sin(th)
+    p = 0.5 * (ct * (r00 + r11) + st * (r10 - r01))
+    x = (r02 * ct + r12 * st) / p
+    y = (r12 * ct - r02 * st) / p
+    return torch.stack((th * (9 / math.pi), (p - 1) / 0.2, x / 0.1, y / 0.1), dim=1)

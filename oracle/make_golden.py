@@ -42,10 +42,23 @@ def make_celeba(B=4, seed=0):
             "phases": fingerprint_log(log)}
 
 
+def make_dsprites(B=6, seed=0):
+    imgs = O.synth_dsprites_images(B, seed)
+    ns, log = R.run_script("dsprites", [imgs], argv=["--batch_size", str(B)], seed=seed,
+                           artefacts={"encoder_pxy_50000.pt": O.dsprites_pxy_state(seed)})
+    names = {"d_loss": "d_loss", "g_loss": "g_loss", "cat_loss": "cat_loss", "cont_loss": "cont_loss",
+             "affine_loss": "affine_loss", "relative_cat_loss": "relative_cat_loss", "total": "info_affine_color_loss"}
+    return {"config": "dsprites", "batch": B, "seed": seed, "torch": torch.__version__,
+            "source": "dSprites/rp.py executed by oracle/ref_runner.py (encoder_pxy_50000.pt = seeded random-init stand-in)",
+            "losses": {k: ns[v].item() for k, v in names.items()},
+            "phases": fingerprint_log(log)}
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
-    for name, fn in (("celeba_b4_seed0", lambda: make_celeba(4, 0)), ("celeba_b6_seed3", lambda: make_celeba(6, 3))):
+    for name, fn in (("celeba_b4_seed0", lambda: make_celeba(4, 0)), ("celeba_b6_seed3", lambda: make_celeba(6, 3)),
+                     ("dsprites_b6_seed0", lambda: make_dsprites(6, 0)), ("dsprites_b8_seed2", lambda: make_dsprites(8, 2))):
         g = fn()
         with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
             json.dump(g, f, indent=1)

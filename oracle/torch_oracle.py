@@ -262,3 +262,223 @@ def summarize(t: torch.Tensor):
     idx = torch.linspace(0, t.numel() - 1, steps=min(8, t.numel())).long()
     return {"sum": float(t.sum()), "l2": float(t.norm()), "absmax": float(t.abs().max()),
             "probe": [float(v) for v in t[idx]]}
+
+
+# --------------------------------------------------------------------------- #
+# dSprites stage 2 (dSprites/rp.py)                                           #
+# --------------------------------------------------------------------------- #
+
+
+def _conv_trunk(cin, slope, sn):
+    wrap = spectral_norm if sn else (lambda m: m)
+    layers = []
+    for a, b in ((cin, 32), (32, 32), (32, 64), (64, 64)):
+        layers += [wrap(nn.Conv2d(a, b, 4, 2, 1)), nn.LeakyReLU(slope, inplace=True)]
+    return nn.Sequential(*layers)
+
+
+class DSpritesEncoderPxy(nn.Module):
+    """dSprites/rp.py:56-82 (frozen stage-1 encoder: zoom / position code)."""
+
+    def __init__(self, channels=1, out_dim=3):
+        super().__init__()
+        self.conv_block = _conv_trunk(channels, 0.1, False)
+        self.fc1 = nn.Linear(1024, out_dim)
+
+    def forward(self, img):
+        x = self.conv_block(img)
+        return self.fc1(x.view(x.shape[0], -1))
+
+
+class DSpritesDiscriminator(nn.Module):
+    """dSprites/rp.py:85-114."""
+
+    def __init__(self, channels=1):
+        super().__init__()
+        self.conv_block = _conv_trunk(channels, 0.2, True)
+        self.fc1 = nn.Sequential(spectral_norm(nn.Linear(1024, 128)), nn.LeakyReLU(0.2, inplace=True))
+        self.fc2 = nn.Linear(128, 1)
+
+    def forward(self, img):
+        x = self.conv_block(img)
+        x = self.fc1(x.view(x.shape[0], -1))
+        return torch.sigmoid(self.fc2(x))
+
+
+class DSpritesGenerator(nn.Module):
+    """dSprites/rp.py:118-152 (registration order: conv_block, fc1, fc2)."""
+
+    def __init__(self, n_classes=3, code_dim=4, channels=1):
+        super().__init__()
+        blk = []
+        for _ in range(3):
+            blk += [nn.ConvTranspose2d(64, 64, 4, 2, 1), nn.BatchNorm2d(64), nn.ReLU()]
+        blk.append(nn.ConvTranspose2d(64, channels, 4, 2, 1))
+        self.conv_block = nn.Sequential(*blk)
+        self.fc1 = nn.Sequential(nn.Linear(n_classes + code_dim, 128), nn.ReLU())
+        self.fc2 = nn.Sequential(nn.Linear(128, 64 * 4 * 4), nn.ReLU())
+
+    def forward(self, z_c):
+        x = self.fc2(self.fc1(z_c))
+        return torch.sigmoid(self.conv_block(x.view(x.shape[0], 64, 4, 4)))
+
+
+class DSpritesEncoder(nn.Module):
+    """dSprites/rp.py:155-190."""
+
+    def __init__(self, n_classes=3, code_dim=4, channels=1):
+        super().__init__()
+        self.conv_block = _conv_trunk(channels, 0.2, True)
+        self.fc1 = nn.Sequential(spectral_norm(nn.Linear(1024, 128)), nn.LeakyReLU(0.2, inplace=True))
+        self.fc2 = nn.Sequential(spectral_norm(nn.Linear(128, 128)), nn.LeakyReLU(0.2, inplace=True))
+        self.cat_layer = nn.Sequential(spectral_norm(nn.Linear(128, n_classes)), nn.Softmax(dim=1))
+        self.cont_layer = nn.Sequential(spectral_norm(nn.Linear(128, code_dim)))
+
+    def forward(self, img):
+        x = self.conv_block(img)
+        x = self.fc2(self.fc1(x.view(x.shape[0], -1)))
+        return self.cat_layer(x), self.cont_layer(x)
+
+
+def mutual_info_loss(c_given_x, c):
+    """dSprites/rp.py:225-232 (eps inside both logs; the target's own entropy is added)."""
+    eps = 1e-8
+    cond = torch.mean(-torch.sum(torch.log(c_given_x + eps) * c, dim=1))
+    ent = torch.mean(-torch.sum(torch.log(c + eps) * c, dim=1))
+    return cond + ent
+
+
+def dsprites_align_matrix(code3):
+    """dSprites/utils_pxy.py:69-87 (get_matrix_pxy_align: translation only, zoom ignored)."""
+    return _shift(code3[:, 1] * 0.1, code3[:, 2] * 0.1)
+
+
+def dsprites_get_matrix(code4):
+    """dSprites/utils_rp.py:38-59 (get_matrix_D) == :94-115 (get_matrix): R(theta) @ Z(p,p) @ T(x,y)."""
+    theta = code4[:, 0] * np.pi / 9
+    p = code4[:, 1] * 0.2 + 1
+    return _rot(theta) @ _zoom(p, p) @ _shift(code4[:, 2] * 0.1, code4[:, 3] * 0.1)
+
+
+def dsprites_affine_regularizer(real_code, trans_code):
+    """dSprites/utils_rp.py:117-147."""
+    rel = dsprites_get_matrix(trans_code[:, :4]) @ torch.inverse(dsprites_get_matrix(real_code[:, :4]))
+    th = torch.atan((rel[:, 1, 0] - rel[:, 0, 1]) / (rel[:, 0, 0] + rel[:, 1, 1]))
+    p = 0.5 * (torch.cos(th) * (rel[:, 0, 0] + rel[:, 1, 1]) + torch.sin(th) * (rel[:, 1, 0] - rel[:, 0, 1]))
+    x = (rel[:, 0, 2] * torch.cos(th) + rel[:, 1, 2] * torch.sin(th)) / p
+    y = (rel[:, 1, 2] * torch.cos(th) - rel[:, 0, 2] * torch.sin(th)) / p
+    out = torch.stack((th / np.pi * 9, (p - 1) / 0.2, x / 0.1, y / 0.1), dim=1)
+    return out.to(real_code.dtype)
+
+
+def build_dsprites(seed=0, device="cpu", dtype=torch.float32):
+    """dSprites/rp.py:255-282: construction order encoder_pxy, encoder, discriminator, generator; the frozen
+    Encoder_pxy then loads a checkpoint -- here a stand-in drawn from seed + 1000 (dsprites_pxy_state)."""
+    torch.manual_seed(seed)
+    Epxy, E, D, G = DSpritesEncoderPxy(), DSpritesEncoder(), DSpritesDiscriminator(), DSpritesGenerator()
+    Epxy.load_state_dict(dsprites_pxy_state(seed))
+    Epxy.eval()
+    for m in (Epxy, E, D, G):
+        m.to(device=device, dtype=dtype)
+    betas = (0.5, 0.999)
+    return {"Epxy": Epxy, "E": E, "D": D, "G": G,
+            "opt_D": torch.optim.Adam(D.parameters(), lr=0.0002, betas=betas),                      # rp.py:277
+            "opt_info": torch.optim.Adam(itertools.chain(G.parameters(), E.parameters()), lr=0.0001, betas=betas)}
+
+
+def dsprites_pxy_state(seed=0):
+    """random-init stand-in for encoder_pxy_50000.pt (unavailable offline)."""
+    g = torch.random.get_rng_state()
+    torch.manual_seed(seed + 1000)
+    sd = {k: v.clone() for k, v in DSpritesEncoderPxy().state_dict().items()}
+    torch.random.set_rng_state(g)
+    return sd
+
+
+def synth_dsprites_images(batch, seed=0):
+    """binary {0,1} uint8 sprites [B,64,64]: one filled axis-aligned ellipse / square per image."""
+    rs = np.random.RandomState(2000 + seed)
+    yy, xx = np.mgrid[0:64, 0:64]
+    out = np.zeros((batch, 64, 64), dtype=np.uint8)
+    for b in range(batch):
+        cx, cy = rs.uniform(20, 44, 2)
+        r = rs.uniform(5, 12)
+        if rs.rand() < 0.5:
+            out[b] = (((xx - cx) / r) ** 2 + ((yy - cy) / (0.7 * r)) ** 2 <= 1).astype(np.uint8)
+        else:
+            out[b] = ((abs(xx - cx) <= r) & (abs(yy - cy) <= r)).astype(np.uint8)
+    return torch.from_numpy(out)
+
+
+def sample_dsprites(rs: np.random.RandomState, batch, code_dim=4, n_classes=3):
+    """host draws in the reference's order: code, labels (phase D, dSprites/rp.py:389-394), then code,
+    labels again (phase info, :424-431)."""
+    d = {}
+    for ph in ("d", "info"):
+        d["code_" + ph] = torch.tensor(rs.uniform(-1, 1, (batch, code_dim)), dtype=torch.float32)
+        d["labels_" + ph] = torch.tensor(rs.randint(0, n_classes, batch), dtype=torch.long)
+    return d
+
+
+def step_dsprites(st, img_u8, draws, record=True):
+    """One iteration of dSprites/rp.py:362-482 on ``img_u8`` uint8 [B,64,64]."""
+    Epxy, E, D, G = st["Epxy"], st["E"], st["D"], st["G"]
+    dt = next(G.parameters()).dtype
+    dev = next(G.parameters()).device
+    bce, mse = nn.BCELoss(), nn.MSELoss()
+    B = img_u8.shape[0]
+    img = img_u8.unsqueeze(1).to(dev).to(dt)                                   # :369-370
+    valid = torch.ones(B, 1, device=dev, dtype=dt)
+    fake = torch.zeros(B, 1, device=dev, dtype=dt)
+    rec = {"phases": []}
+
+    def aligned():
+        code = Epxy(img)                                                       # :374 (grad-tracked, frozen)
+        inv = torch.inverse(dsprites_align_matrix(code))
+        return stn(img, inv[:, 0:2])                                           # :375-377
+
+    # ---- phase D  (:379-419)
+    align_img = aligned()
+    code = draws["code_d"].to(dev, dt)
+    lab = one_hot(draws["labels_d"], 3, code)
+    trans_img = stn(align_img, dsprites_get_matrix(code[:, :4])[:, 0:2])       # :399-400
+    gen = G(torch.cat((lab, code), dim=1))
+    d_real = D(trans_img)            # order matters: every D forward advances the spectral-norm u, v (:410-411)
+    d_fake = D(gen.detach())
+    d_loss = (bce(d_fake, fake) + bce(d_real, valid)) / 2
+    st["opt_D"].zero_grad()
+    d_loss.backward()
+    if record:
+        rec["phases"].append({"name": "D", "grads": _snap(st["opt_D"])})
+    st["opt_D"].step()
+    if record:
+        rec["phases"][-1]["params_after"] = _params(st["opt_D"])
+        rec["phases"][-1]["state_after"] = {k: {n: v.detach().clone() for n, v in st[k].state_dict().items()}
+                                            for k in ("G", "D", "E")}
+
+    # ---- phase info  (:424-482)
+    code = draws["code_info"].to(dev, dt)
+    lab = one_hot(draws["labels_info"], 3, code)
+    gen = G(torch.cat((lab, code), dim=1))
+    rec_cat, rec_cont = E(gen)
+    g_loss = bce(D(gen), valid)
+    cat_loss = mutual_info_loss(rec_cat, lab)
+    cont_loss = mse(rec_cont, code)
+    align_img = aligned()
+    trans_img = stn(align_img, dsprites_get_matrix(code[:, :4])[:, 0:2])
+    align_cat, align_cont = E(align_img)
+    trans_cat, trans_cont = E(trans_img)
+    affine_loss = mse(dsprites_affine_regularizer(align_cont, trans_cont), code)
+    rel_cat_loss = mutual_info_loss(trans_cat, align_cat.detach())             # Variable(..., requires_grad=False)
+    total = cat_loss + cont_loss + affine_loss + g_loss + rel_cat_loss
+    st["opt_info"].zero_grad()
+    total.backward()
+    if record:
+        rec["phases"].append({"name": "info", "grads": _snap(st["opt_info"])})
+    st["opt_info"].step()
+    if record:
+        rec["phases"][-1]["params_after"] = _params(st["opt_info"])
+    rec["losses"] = {"d_loss": d_loss.item(), "g_loss": g_loss.item(), "cat_loss": cat_loss.item(),
+                     "cont_loss": cont_loss.item(), "affine_loss": affine_loss.item(),
+                     "relative_cat_loss": rel_cat_loss.item(), "total": total.item()}
+    return rec

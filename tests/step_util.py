@@ -59,7 +59,7 @@ ZERO_GRAD = {"G.conv_blocks.1.bias": "G.conv_blocks.1.weight", "G.conv_blocks.4.
              "G.conv_blocks.7.bias": "G.conv_blocks.7.weight"}
 
 
-def phase_errors(names, ours_grads, ref_grads):
+def phase_errors(names, ours_grads, ref_grads, zero_grad=None):
     """-> {name: (max_err, l2_err, cosine)}.  Zero-gradient tensors use their sibling weight's scale
     (l2 / cosine = None); so do tensors with fewer than 16 elements (the [3] bias of G's last layer is
     a sum of 4096*B random-sign terms: ill-conditioned as a 3-vector, well-defined as one more column
@@ -67,12 +67,49 @@ def phase_errors(names, ours_grads, ref_grads):
     refs = dict(zip(names, ref_grads))
     out = {}
     for n, a, b in zip(names, ours_grads, ref_grads):
-        sib = ZERO_GRAD.get(n)
+        zg = ZERO_GRAD if zero_grad is None else zero_grad
+        sib = zg.get(n)
         if sib is None and b.numel() < 16 and n.endswith(".bias"):
-            sib = n[:-5] + ".weight"
+            sib = n[:-5] + ".weight" if n[:-5] + ".weight" in refs else n[:-5] + ".weight_orig"
         if sib is not None:
             floor = refs[sib].abs().max().item()
-            out[n] = (tensor_err(a, b, floor), None, None if n in ZERO_GRAD else "small")
+            out[n] = (tensor_err(a, b, floor), None, None if n in zg else "small")
         else:
             out[n] = (tensor_err(a, b), l2_err(a, b), cosine(a, b))
     return out
+
+
+# ---- dSprites -------------------------------------------------------------------------------------------
+def run_pair_dsprites(dev, B, precision, oracle_dtype=torch.float64, seed=0, sync=True):
+    """the dSprites stage-2 step (dSprites/rp.py): oracle vs OUR step; phase info of ours restarts from the
+    oracle's post-phase-D state."""
+    from eadgan_b200.steps.dsprites import DSpritesStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = precision
+    imgs = O.synth_dsprites_images(B, seed).to(dev)
+    draws = O.sample_dsprites(np.random.RandomState(seed), B)
+    st = O.build_dsprites(seed=seed, device=dev, dtype=oracle_dtype)
+    ref = O.step_dsprites(st, imgs, draws)
+    ours = DSpritesStep(seed=seed, device=dev, pxy_state=O.dsprites_pxy_state(seed))
+
+    def after_phase(i):
+        if sync and i == 0:
+            snap = ref["phases"][0]["state_after"]
+            for key, net in (("G", ours.G), ("D", ours.D), ("E", ours.E)):
+                net.load_state_dict({k: v.to(torch.float32) if v.is_floating_point() else v for k, v in snap[key].items()})
+
+    rec = []
+    losses = ours(imgs, draws["code_d"].to(dev), draws["labels_d"].to(dev), draws["code_info"].to(dev),
+                  draws["labels_info"].to(dev), record=rec, after_phase=after_phase)
+    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
+
+
+def dsprites_grad_names(step):
+    d = ["D." + n for n, _ in step.D.named_parameters()]
+    g = ["G." + n for n, _ in step.G.named_parameters()]
+    e = ["E." + n for n, _ in step.E.named_parameters()]
+    return [d, g + e]
+
+
+DSPRITES_ZERO_GRAD = {"G.conv_block.0.bias": "G.conv_block.0.weight", "G.conv_block.3.bias": "G.conv_block.3.weight",
+                      "G.conv_block.6.bias": "G.conv_block.6.weight"}

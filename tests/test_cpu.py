@@ -57,6 +57,27 @@ def test_oracle_reproduces_reference_golden(name):
             _check_fp(t, fp, rt_p)
 
 
+@pytest.mark.parametrize("name", ["dsprites_b6_seed0", "dsprites_b8_seed2"])
+def test_dsprites_oracle_reproduces_reference_golden(name):
+    """the dSprites stage-2 restatement vs fixtures produced by executing dSprites/rp.py itself."""
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    B, seed = g["batch"], g["seed"]
+    torch.set_num_threads(8)
+    st = O.build_dsprites(seed=seed)
+    rec = O.step_dsprites(st, O.synth_dsprites_images(B, seed), O.sample_dsprites(np.random.RandomState(seed), B))
+    for k, v in g["losses"].items():
+        assert _close(rec["losses"][k], v, 1e-5), (k, rec["losses"][k], v)
+    assert len(rec["phases"]) == len(g["phases"]) == 2
+    for ph, gph in zip(rec["phases"], g["phases"]):
+        assert len(ph["grads"]) == len(gph["grads"])
+        for t, fp in zip(ph["grads"], gph["grads"]):
+            _check_fp(t, fp, 1e-4)
+        for t, fp in zip(ph["params_after"], gph["params_after"]):
+            _check_fp(t, fp, 1e-4)
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
 def test_oracle_classes_equal_reference_classes():
     """key-for-key, bit-for-bit equality of the restated modules with the AST-extracted reference classes."""
@@ -100,6 +121,39 @@ def test_reference_affine_glue_matches():
                            (affine.celeba_matrix, affine.celeba_relative_code)):
         assert (impl_m(c1[:, :5]) - m_ref).abs().max() <= 1e-6
         assert (impl_r(c1, c2) - r_ref).abs().max() <= 1e-4
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
+def test_reference_dsprites_affine_glue_matches():
+    """dSprites/utils_pxy.py + utils_rp.py executed as is vs the oracle restatement and the device-side
+    closed-form glue of the product (eadgan_b200/affine.py)."""
+    import importlib.util
+    from oracle import torch_oracle as O
+    from eadgan_b200 import affine
+    saved = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        mods = {}
+        for name in ("utils_pxy", "utils_rp"):
+            spec = importlib.util.spec_from_file_location("ref_" + name, f"/root/reference/dSprites/{name}.py")
+            mods[name] = importlib.util.module_from_spec(spec)
+            mods[name].np = np          # utils_rp.py uses np without importing it (the scripts star-import numpy first)
+            spec.loader.exec_module(mods[name])
+        torch.manual_seed(1)
+        c1, c2, c3 = torch.rand(9, 4) * 2 - 1, torch.rand(9, 4) * 2 - 1, torch.rand(9, 3) * 2 - 1
+        m_ref = mods["utils_rp"].get_matrix_D(c1)
+        m2_ref = mods["utils_rp"].get_matrix(c1)
+        al_ref = torch.inverse(mods["utils_pxy"].get_matrix_pxy_align(c3))
+        r_ref = mods["utils_rp"].affine_regularzier(c1, c2)
+    finally:
+        torch.Tensor.cuda = saved
+    assert torch.equal(m_ref, m2_ref)
+    assert (O.dsprites_get_matrix(c1) - m_ref).abs().max() <= 1e-6
+    assert (affine.dsprites_matrix23(c1) - m_ref[:, 0:2]).abs().max() <= 1e-6
+    assert (torch.inverse(O.dsprites_align_matrix(c3)) - al_ref).abs().max() <= 1e-6
+    assert (affine.dsprites_align_inverse(c3) - al_ref[:, 0:2]).abs().max() <= 1e-6
+    assert (O.dsprites_affine_regularizer(c1, c2) - r_ref).abs().max() <= 1e-5
+    assert (affine.dsprites_relative_code(c1, c2) - r_ref).abs().max() <= 1e-4
 
 
 def test_product_modules_mirror_reference_layout():
