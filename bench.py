@@ -182,7 +182,7 @@ def main():
         return ms
 
     eager_step = step
-    use_graph = not args.no_graph and world == 1
+    use_graph = not args.no_graph   # under DP the NCCL all-reduces (gradient buckets, SyncBN) are captured too
     if use_graph:
         from eadgan_b200.graph import GraphedStep
         step = GraphedStep(eager_step, resident[0], warmup=args.warmup)   # warm-up steps run inside, eagerly

@@ -41,7 +41,7 @@ def test_graphed_step_matches_eager(cuda, prec):
             if a.is_floating_point():
                 d = (a - b).abs()
                 assert float(d.max()) <= 6e-3, (n, float(d.max()))
-                assert float(d.mean()) <= 2e-5, (n, float(d.mean()))
+                assert float(d.mean()) <= (2e-5 if prec == "bf16" else 1e-4), (n, float(d.mean()))
     # python-side step mirrors follow the device counter
     st = next(iter(graphed.opt_G.state.values()))
     assert st["step"] == W + K
