@@ -113,3 +113,73 @@ def dsprites_relative_code(real_code, trans_code):
     x = (r02 * ct + r12 * st) / p
     y = (r12 * ct - r02 * st) / p
     return torch.stack((th * (9 / math.pi), (p - 1) / 0.2, x / 0.1, y / 0.1), dim=1)
+
+
+# ---- colored dSprites (colored_dSprites/utils_rp_color.py) -------------------------------------------------
+def colored_relative_code(real_code, trans_code):
+    """affine_color_regularzier of colored_dSprites/utils_rp_color.py:99-139: entries 0..3 as in
+    dsprites_relative_code; entries 4..6 are the ratio of the colour gains c * 0.5 + 1 mapped back to a code."""
+    aff = dsprites_relative_code(real_code[:, :4], trans_code[:, :4])
+    rel = (trans_code[:, 4:] * 0.5 + 1) / (real_code[:, 4:] * 0.5 + 1)
+    return torch.cat((aff, (rel - 1) / 0.5), dim=1)
+
+
+# ---- MNIST (MNIST/utils_rpqmnxy.py) ------------------------------------------------------------------------
+def _rzst_parts(code7):
+    """(a, b, c, d, tx, ty) of R(theta) diag(p, q, 1) Skew(m, n) T(x, y)  (MNIST/utils_rpqmnxy.py:46-60,87-114)."""
+    theta, p, q = code7[:, 0] * (math.pi / 9), code7[:, 1] * 0.2 + 1, code7[:, 2] * 0.2 + 1
+    m, n = code7[:, 3] * 0.2, code7[:, 4] * 0.2
+    x, y = code7[:, 5] * 0.1, code7[:, 6] * 0.1
+    c, s = torch.cos(theta), torch.sin(theta)
+    # R Z = [[c p, -s q], [s p, c q]];  (R Z) S with S = [[1, m], [n, 1]]
+    a, b = c * p - s * q * n, c * p * m - s * q
+    cc, d = s * p + c * q * n, s * p * m + c * q
+    return a, b, cc, d, a * x + b * y, cc * x + d * y
+
+
+def mnist_matrix23(code7):
+    a, b, c, d, tx, ty = _rzst_parts(code7)
+    return torch.stack((torch.stack((a, b, tx), dim=1), torch.stack((c, d, ty), dim=1)), dim=1)
+
+
+def mnist_relative_rows(real_code, trans_code):
+    """top two rows of M(trans) @ inverse(M(real)), flattened to [B, 6] -- the approximator's input
+    (MNIST/utils_rpqmnxy.py:123-129); closed-form affine inverse, no host round trip."""
+    a1, b1, c1, d1, x1, y1 = _rzst_parts(real_code)
+    a2, b2, c2, d2, x2, y2 = _rzst_parts(trans_code)
+    det = a1 * d1 - b1 * c1
+    ia, ib, ic, id_ = d1 / det, -b1 / det, -c1 / det, a1 / det
+    itx, ity = -(ia * x1 + ib * y1), -(ic * x1 + id_ * y1)
+    r00, r01 = a2 * ia + b2 * ic, a2 * ib + b2 * id_
+    r10, r11 = c2 * ia + d2 * ic, c2 * ib + d2 * id_
+    r02, r12 = a2 * itx + b2 * ity + x2, c2 * itx + d2 * ity + y2
+    return torch.stack((r00, r01, r02, r10, r11, r12), dim=1)
+
+
+def mnist_code_from_params(pred):
+    """from_affine_para_2_latent_vector (MNIST/utils_rpqmnxy.py:64-84)."""
+    return torch.stack((pred[:, 0] * (9 / math.pi), (pred[:, 1] - 1) / 0.2, (pred[:, 2] - 1) / 0.2, pred[:, 3] / 0.2,
+                        pred[:, 4] / 0.2, pred[:, 5] / 0.1, pred[:, 6] / 0.1), dim=1)
+
+
+# ---- stage 1 (dSprites/utils_pxy.py, colored_dSprites/utils_pxy.py) -----------------------------------------
+def pxy_matrix23(code):
+    """get_matrix_pxy(code)[:, 0:2] = (Z(p,p) @ T(x,y))[:, 0:2]  (dSprites/utils_pxy.py:49-66)."""
+    p = code[:, 0] * 0.1 + 1
+    zero = torch.zeros_like(p)
+    return torch.stack((torch.stack((p, zero, p * (code[:, 1] * 0.1)), dim=1),
+                        torch.stack((zero, p, p * (code[:, 2] * 0.1)), dim=1)), dim=1)
+
+
+def pxy_relative_code(real_code, trans_code):
+    """affine_regularzier_pxy (dSprites/utils_pxy.py:107-126, colored_dSprites/utils_pxy.py:150-175) in closed
+    form: M = [[p,0,px],[0,p,py]] so M2 @ inverse(M1) has zoom p2/p1 and translation p2 (x2 - x1)."""
+    p1, p2 = real_code[:, 0] * 0.1 + 1, trans_code[:, 0] * 0.1 + 1
+    rp = p2 / p1
+    rx = p2 * (trans_code[:, 1] * 0.1 - real_code[:, 1] * 0.1) / rp
+    ry = p2 * (trans_code[:, 2] * 0.1 - real_code[:, 2] * 0.1) / rp
+    out = torch.stack(((rp - 1) / 0.1, rx / 0.1, ry / 0.1), dim=1)
+    if real_code.shape[1] > 3:
+        rel = (trans_code[:, 3:] * 0.1 + 1) / (real_code[:, 3:] * 0.1 + 1)
+        out = torch.cat((out, (rel - 1) / 0.1), dim=1)
+    return out

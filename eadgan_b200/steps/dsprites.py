@@ -57,14 +57,14 @@ class Discriminator(torch.nn.Module):
 
 
 class Generator(torch.nn.Module):
-    def __init__(self, channels=1):
+    def __init__(self, channels=1, code_dim=CODE):
         super().__init__()
         blk = []
         for _ in range(3):
             blk += [nn.ConvTranspose2d(64, 64, 4, 2, 1), nn.BatchNorm2d(64), nn.ReLU()]
         blk.append(nn.ConvTranspose2d(64, channels, 4, 2, 1))
         self.conv_block = nn.Sequential(*blk)                 # registration order of rp.py:128-146
-        self.fc1 = nn.Sequential(nn.Linear(N_CLASSES + CODE, 128), nn.ReLU())
+        self.fc1 = nn.Sequential(nn.Linear(N_CLASSES + code_dim, 128), nn.ReLU())
         self.fc2 = nn.Sequential(nn.Linear(128, 64 * 4 * 4), nn.ReLU())
 
     def forward(self, z_c):
@@ -74,13 +74,13 @@ class Generator(torch.nn.Module):
 
 
 class Encoder(torch.nn.Module):
-    def __init__(self, channels=1):
+    def __init__(self, channels=1, code_dim=CODE):
         super().__init__()
         self.conv_block = _trunk(channels, 0.2, True)
         self.fc1 = nn.Sequential(nn.spectral_norm(nn.Linear(1024, 128)), nn.LeakyReLU(0.2, inplace=True))
         self.fc2 = nn.Sequential(nn.spectral_norm(nn.Linear(128, 128)), nn.LeakyReLU(0.2, inplace=True))
         self.cat_layer = nn.Sequential(nn.spectral_norm(nn.Linear(128, N_CLASSES)), nn.Softmax())
-        self.cont_layer = nn.Sequential(nn.spectral_norm(nn.Linear(128, CODE)))
+        self.cont_layer = nn.Sequential(nn.spectral_norm(nn.Linear(128, code_dim)))
 
     def forward(self, img):
         x = self.conv_block(img)

@@ -54,11 +54,51 @@ def make_dsprites(B=6, seed=0):
             "phases": fingerprint_log(log)}
 
 
+def make_colored(B=6, seed=0):
+    imgs = O.synth_dsprites_images(B, seed)
+    ns, log = R.run_script("colored", [imgs], argv=["--batch_size", str(B)], seed=seed,
+                           artefacts={"encoder_pxy_color_50000.pt": O.dsprites_pxy_state(seed, colored=True)})
+    names = {"d_loss": "d_loss", "g_loss": "g_loss", "cat_loss": "cat_loss", "cont_loss": "cont_loss",
+             "affine_loss": "affine_color_loss", "relative_cat_loss": "relative_cat_loss",
+             "total": "info_affine_color_loss"}
+    return {"config": "colored", "batch": B, "seed": seed, "torch": torch.__version__,
+            "source": "colored_dSprites/rp_color.py executed by oracle/ref_runner.py "
+                      "(encoder_pxy_color_50000.pt = seeded random-init stand-in)",
+            "losses": {k: ns[v].item() for k, v in names.items()},
+            "phases": fingerprint_log(log)}
+
+
+def make_mnist(B=8, seed=0):
+    imgs = O.synth_mnist_images(B, seed)
+    ns, log = R.run_script("mnist", [(imgs, torch.zeros(B, dtype=torch.long))], argv=["--batch_size", str(B)],
+                           seed=seed, artefacts={"rpqmnxy_approximator.pt": O.mnist_approximator_state(seed)})
+    return {"config": "mnist", "batch": B, "seed": seed, "torch": torch.__version__,
+            "source": "MNIST/EAD-GAN_rpqmnxy.py executed by oracle/ref_runner.py "
+                      "(rpqmnxy_approximator.pt = seeded random-init stand-in)",
+            "losses": {"g_loss": ns["g_loss"].item(), "d_loss": ns["d_loss"].item(),
+                       "info_loss": ns["info_loss"].item()},
+            "phases": fingerprint_log(log)}
+
+
+def make_pxy(B=8, seed=0, colored=False):
+    imgs = O.synth_dsprites_images(B, seed)
+    ns, log = R.run_script("pxy_color" if colored else "pxy", [imgs], argv=["--batch_size", str(B)], seed=seed)
+    return {"config": "pxy_color" if colored else "pxy", "batch": B, "seed": seed, "torch": torch.__version__,
+            "source": ("colored_dSprites/pxy_color.py" if colored else "dSprites/pxy.py") + " executed by oracle/ref_runner.py",
+            "losses": {"affine_loss": ns["affine_loss"].item()},
+            "phases": fingerprint_log(log)}
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     for name, fn in (("celeba_b4_seed0", lambda: make_celeba(4, 0)), ("celeba_b6_seed3", lambda: make_celeba(6, 3)),
-                     ("dsprites_b6_seed0", lambda: make_dsprites(6, 0)), ("dsprites_b8_seed2", lambda: make_dsprites(8, 2))):
+                     ("dsprites_b6_seed0", lambda: make_dsprites(6, 0)), ("dsprites_b8_seed2", lambda: make_dsprites(8, 2)),
+                     ("colored_b6_seed0", lambda: make_colored(6, 0)), ("colored_b8_seed1", lambda: make_colored(8, 1)),
+                     ("mnist_b8_seed0", lambda: make_mnist(8, 0)), ("mnist_b64_seed1", lambda: make_mnist(64, 1)),
+                     ("pxy_b8_seed0", lambda: make_pxy(8, 0)), ("pxy_color_b8_seed0", lambda: make_pxy(8, 0, True))):
+        if sys.argv[1:] and not any(name.startswith(a) for a in sys.argv[1:]):
+            continue
         g = fn()
         with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
             json.dump(g, f, indent=1)

@@ -113,3 +113,65 @@ def dsprites_grad_names(step):
 
 DSPRITES_ZERO_GRAD = {"G.conv_block.0.bias": "G.conv_block.0.weight", "G.conv_block.3.bias": "G.conv_block.3.weight",
                       "G.conv_block.6.bias": "G.conv_block.6.weight"}
+
+
+# ---- colored dSprites ------------------------------------------------------------------------------------
+def run_pair_colored(dev, B, precision, oracle_dtype=torch.float64, seed=0, sync=True):
+    """the colored-dSprites stage-2 step (colored_dSprites/rp_color.py): oracle vs OUR step."""
+    from eadgan_b200.steps.colored import ColoredDSpritesStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = precision
+    imgs = O.synth_dsprites_images(B, seed).to(dev)
+    draws = O.sample_colored(np.random.RandomState(seed), B)
+    st = O.build_dsprites(seed=seed, device=dev, dtype=oracle_dtype, colored=True)
+    ref = O.step_colored(st, imgs, draws)
+    ours = ColoredDSpritesStep(seed=seed, device=dev, pxy_state=O.dsprites_pxy_state(seed, colored=True))
+
+    def after_phase(i):
+        if sync and i == 0:
+            snap = ref["phases"][0]["state_after"]
+            for key, net in (("G", ours.G), ("D", ours.D), ("E", ours.E)):
+                net.load_state_dict({k: v.to(torch.float32) if v.is_floating_point() else v for k, v in snap[key].items()})
+
+    rec = []
+    losses = ours(imgs, draws["color"].to(dev), draws["code_d"].to(dev), draws["labels_d"].to(dev),
+                  draws["code_info"].to(dev), draws["labels_info"].to(dev), record=rec, after_phase=after_phase)
+    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
+
+
+# ---- MNIST -------------------------------------------------------------------------------------------------
+def run_pair_mnist(dev, B, precision, oracle_dtype=torch.float64, seed=0, sync=True):
+    """the MNIST step (MNIST/EAD-GAN_rpqmnxy.py): oracle vs OUR step, phases restarted from the oracle's state."""
+    from eadgan_b200.steps.mnist import MnistStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = precision
+    imgs = O.synth_mnist_images(B, seed).to(dev)
+    draws = O.sample_mnist(np.random.RandomState(seed), B)
+    st = O.build_mnist(seed=seed, device=dev, dtype=oracle_dtype)
+    ref = O.step_mnist(st, imgs, draws)
+    ours = MnistStep(seed=seed, device=dev, approximator_state=O.mnist_approximator_state(seed))
+
+    def after_phase(i):
+        if not sync:
+            return
+        snap = ref["phases"][i]["state_after"]
+        for key, net in (("G", ours.G), ("D", ours.D), ("E", ours.E)):
+            net.load_state_dict({k: v.to(torch.float32) if v.is_floating_point() else v for k, v in snap[key].items()})
+
+    rec = []
+    losses = ours(imgs, draws["z"].to(dev), draws["code"].to(dev), draws["labels"].to(dev), record=rec,
+                  after_phase=after_phase)
+    return ref, rec, {k: float(v) for k, v in losses.items()}, st, ours
+
+
+def mnist_grad_names(step):
+    g = ["G." + n for n, _ in step.G.named_parameters()]
+    d = ["D." + n for n, _ in step.D.named_parameters()]
+    e = ["E." + n for n, _ in step.E.named_parameters()]
+    return [g, d, g + e]
+
+
+# conv biases in front of a train-mode BatchNorm (G: conv_blocks.2 -> BN .3, conv_blocks.6 -> BN .7; the l1 Linear
+# feeds BatchNorm .0 directly): mathematically zero gradients
+MNIST_ZERO_GRAD = {"G.conv_blocks.2.bias": "G.conv_blocks.2.weight", "G.conv_blocks.6.bias": "G.conv_blocks.6.weight",
+                   "G.l1.0.bias": "G.l1.0.weight"}

@@ -78,6 +78,99 @@ def test_dsprites_oracle_reproduces_reference_golden(name):
             _check_fp(t, fp, 1e-4)
 
 
+@pytest.mark.parametrize("name", ["colored_b6_seed0", "colored_b8_seed1"])
+def test_colored_oracle_reproduces_reference_golden(name):
+    """the colored-dSprites stage-2 restatement vs fixtures produced by executing colored_dSprites/rp_color.py."""
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    B, seed = g["batch"], g["seed"]
+    torch.set_num_threads(8)
+    st = O.build_dsprites(seed=seed, colored=True)
+    rec = O.step_colored(st, O.synth_dsprites_images(B, seed), O.sample_colored(np.random.RandomState(seed), B))
+    for k, v in g["losses"].items():
+        assert _close(rec["losses"][k], v, 1e-5), (k, rec["losses"][k], v)
+    assert len(rec["phases"]) == len(g["phases"]) == 2
+    for ph, gph in zip(rec["phases"], g["phases"]):
+        assert len(ph["grads"]) == len(gph["grads"])
+        for t, fp in zip(ph["grads"], gph["grads"]):
+            _check_fp(t, fp, 1e-4)
+        for t, fp in zip(ph["params_after"], gph["params_after"]):
+            _check_fp(t, fp, 1e-4)
+
+
+@pytest.mark.parametrize("name", ["mnist_b8_seed0", "mnist_b64_seed1"])
+def test_mnist_oracle_reproduces_reference_golden(name):
+    """BASELINE configs[0]: the MNIST restatement vs fixtures produced by executing MNIST/EAD-GAN_rpqmnxy.py
+    (batch 64 is the configuration's own batch size)."""
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    B, seed = g["batch"], g["seed"]
+    torch.set_num_threads(8)
+    st = O.build_mnist(seed=seed)
+    rec = O.step_mnist(st, O.synth_mnist_images(B, seed), O.sample_mnist(np.random.RandomState(seed), B))
+    for k, v in g["losses"].items():
+        assert _close(rec["losses"][k], v, 1e-5), (k, rec["losses"][k], v)
+    assert len(rec["phases"]) == len(g["phases"]) == 3
+    for ph, gph, rt in zip(rec["phases"], g["phases"], (1e-4, 1e-4, 2e-3)):
+        assert len(ph["grads"]) == len(gph["grads"])
+        for t, fp in zip(ph["grads"], gph["grads"]):
+            if (t is None) != (fp is None):
+                raise AssertionError("gradient presence differs from the reference run")
+            if t is not None:
+                _check_fp(t, fp, rt)
+        for t, fp in zip(ph["params_after"], gph["params_after"]):
+            _check_fp(t, fp, rt)
+
+
+def test_mnist_affine_glue_matches_oracle():
+    from eadgan_b200 import affine
+    from oracle import torch_oracle as O
+    g = torch.Generator().manual_seed(7)
+    c1, c2 = torch.rand(32, 7, generator=g) * 2 - 1, torch.rand(32, 7, generator=g) * 2 - 1
+    assert (affine.mnist_matrix23(c1) - O.mnist_get_matrix(c1)[:, 0:2]).abs().max() <= 1e-6
+    rel = O.mnist_get_matrix(c2) @ torch.inverse(O.mnist_get_matrix(c1))
+    assert (affine.mnist_relative_rows(c1, c2) - torch.cat((rel[:, 0], rel[:, 1]), dim=1)).abs().max() <= 1e-5
+    A = O.MnistAffineApproximator()
+    want = O.mnist_affine_regularizer(c1, c2, A)
+    got = affine.mnist_code_from_params(A(affine.mnist_relative_rows(c1, c2)))
+    assert (got - want).abs().max() <= 1e-4
+
+
+@pytest.mark.parametrize("name,colored", [("pxy_b8_seed0", False), ("pxy_color_b8_seed0", True)])
+def test_pxy_oracle_reproduces_reference_golden(name, colored):
+    """stage 1 (dSprites/pxy.py, colored_dSprites/pxy_color.py) restatement vs the scripts' own outputs"""
+    from eadgan_b200 import affine
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, name + ".json")) as f:
+        g = json.load(f)
+    B, seed = g["batch"], g["seed"]
+    st = O.build_pxy(seed=seed, colored=colored)
+    rec = O.step_pxy(st, O.synth_dsprites_images(B, seed), O.sample_pxy(np.random.RandomState(seed), B, colored))
+    assert _close(rec["losses"]["affine_loss"], g["losses"]["affine_loss"], 1e-5)
+    for t, fp in zip(rec["phases"][0]["grads"], g["phases"][0]["grads"]):
+        _check_fp(t, fp, 1e-4)
+    for t, fp in zip(rec["phases"][0]["params_after"], g["phases"][0]["params_after"]):
+        _check_fp(t, fp, 1e-4)
+    # device-side glue vs the oracle's matrix form
+    gen = torch.Generator().manual_seed(3)
+    k = 6 if colored else 3
+    c1, c2 = torch.rand(16, k, generator=gen) * 2 - 1, torch.rand(16, k, generator=gen) * 2 - 1
+    assert (affine.pxy_matrix23(c1) - O.pxy_get_matrix(c1)[:, 0:2]).abs().max() <= 1e-6
+    assert (affine.pxy_relative_code(c1, c2) - O.pxy_affine_regularizer(c1, c2)).abs().max() <= 1e-4
+
+
+def test_colored_affine_glue_matches_oracle():
+    """device-side restatement (eadgan_b200/affine.py) of affine_color_regularzier vs the oracle's (which is
+    pinned to colored_dSprites/rp_color.py through the golden fixtures above)."""
+    from eadgan_b200 import affine
+    from oracle import torch_oracle as O
+    g = torch.Generator().manual_seed(5)
+    c1, c2 = torch.rand(32, 7, generator=g) * 2 - 1, torch.rand(32, 7, generator=g) * 2 - 1
+    assert (affine.colored_relative_code(c1, c2) - O.colored_affine_color_regularizer(c1, c2)).abs().max() <= 1e-4
+
+
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
 def test_oracle_classes_equal_reference_classes():
     """key-for-key, bit-for-bit equality of the restated modules with the AST-extracted reference classes."""
