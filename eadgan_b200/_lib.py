@@ -52,7 +52,7 @@ _I, _F, _D, _L = C.c_int, C.c_float, C.c_double, C.c_int64
 _PROTOS = {
     "eadgan_conv_fprop": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _T4, _I, _F, _P],
     "eadgan_conv_dgrad": [C.POINTER(ConvDesc), _T4, _P, _P, _I, _F, _T4, _T4, _I, _F, _P],
-    "eadgan_conv_wgrad": [C.POINTER(ConvDesc), _T4, _T4, _P, _P],
+    "eadgan_conv_wgrad": [C.POINTER(ConvDesc), _T4, _T4, _P, _P, C.c_size_t, _P],
     "eadgan_channel_sum": [_T4, _I, _I, _I, _I, _P, _P],
     "eadgan_tc_pack_w_fprop": [_P, _P, _I, _I, _I, _P, _P],
     "eadgan_tc_pack_w_dgrad": [_P, _P, _I, _I, _I, _P, _P],
@@ -101,6 +101,7 @@ _SPECIAL = {
     "eadgan_sm_count": ([], C.c_int),
     "eadgan_kernel_launches": ([], C.c_int64),
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
+    "eadgan_conv_wgrad_workspace": ([C.POINTER(ConvDesc)], C.c_size_t),
     "eadgan_tc_dense_wgrad_workspace": ([_I, _I], C.c_size_t),
     "eadgan_spectral_norm_scratch_floats": ([_I, _I, _I], C.c_size_t),
 }

@@ -399,9 +399,8 @@ class _ChainFn(torch.autograd.Function):
                         x_big = dz
                     dw = tc.wgrad(xb, dy_small.padded(), c_real=d.c if ca != d.c else 0)
                 else:
-                    dw = torch.zeros_like(sv["w"])
-                    xd, dyd = t4(x_big.view()), t4(dy_small.view())
-                    call("eadgan_conv_wgrad", C.byref(d), C.byref(xd), C.byref(dyd), ptr(dw), st_)
+                    dw = torch.empty_like(sv["w"])
+                    Fn.conv_wgrad(d, t4(x_big.view()), t4(dy_small.view()), dw)
                 if need_dx:
                     direction = "dgrad" if st.kind == "conv" else "fprop"
                     tc_dx = impl == "tc" and _tc_ok(d, direction) and (not fuse or sv["inp"].fmt == "pad")

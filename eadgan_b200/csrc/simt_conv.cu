@@ -23,7 +23,7 @@ struct ConvArgs {
   float mask_slope;
   const float* w;
   const float* bias;
-  float* dw;
+  float* dw; float* partial;
   int act;
   float slope;
   int M, N, K;       // GEMM extents of this direction
@@ -266,11 +266,19 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(const ConvArgs P) {
     for (int j = 0; j < 4; ++j) {
       const int kk = kk0 + ty * 4 + j;
       if (kk >= P.N) continue;
-      if (gridDim.z == 1)
-        P.dw[(int64_t)ko * P.N + kk] += acc[i][j];
-      else
-        atomicAdd(&P.dw[(int64_t)ko * P.N + kk], acc[i][j]);
+      // split z writes its own slab of the workspace (or dw itself when there is one split): no atomics, so
+      // the result is run-to-run deterministic; wgrad_sum_kernel adds the slabs in a fixed order
+      float* dst = gridDim.z == 1 ? P.dw : P.partial + (int64_t)blockIdx.z * P.M * P.N;
+      dst[(int64_t)ko * P.N + kk] = acc[i][j];
     }
+  }
+}
+
+__global__ void wgrad_sum_kernel(const float* __restrict__ partial, int splits, int64_t numel, float* __restrict__ dw) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < numel; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += partial[(int64_t)sp * numel + i];
+    dw[i] = s;
   }
 }
 
@@ -357,26 +365,56 @@ extern "C" int eadgan_conv_dgrad(const eadgan_conv_desc* d, const eadgan_tensor4
   return 0;
 }
 
+namespace {
+// split of the reduction (pixel) dimension of the wgrad GEMM: enough CTAs to fill the machine, at least 4
+// BK-chunks of work per split
+void wgrad_split(const eadgan_conv_desc* d, int* splits, int* mps) {
+  const int M = d->k, N = d->c * d->r * d->s, K = d->n * d->p * d->q;
+  const int tiles = ((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+  const int target = 4 * eg_sm_count();
+  int sp = (target + tiles - 1) / tiles;
+  const int max_splits = (K + 4 * BK - 1) / (4 * BK);
+  if (sp > max_splits) sp = max_splits;
+  if (sp < 1) sp = 1;
+  int m = (K + sp - 1) / sp;
+  m = ((m + BK - 1) / BK) * BK;
+  *splits = (K + m - 1) / m;
+  *mps = m;
+}
+}  // namespace
+
+extern "C" size_t eadgan_conv_wgrad_workspace(const eadgan_conv_desc* d) {
+  if (!d || check_desc(d)) return 0;
+  int splits, mps;
+  wgrad_split(d, &splits, &mps);
+  return splits > 1 ? (size_t)splits * d->k * d->c * d->r * d->s * sizeof(float) : 0;
+}
+
 extern "C" int eadgan_conv_wgrad(const eadgan_conv_desc* d, const eadgan_tensor4* x,
-                                 const eadgan_tensor4* dy, float* dw, void* stream) {
+                                 const eadgan_tensor4* dy, float* dw, void* workspace, size_t ws_bytes,
+                                 void* stream) {
   if (int e = check_desc(d)) return e;
   EG_REQUIRE(x && dy && x->ptr && dy->ptr && dw, EADGAN_ERR_INVALID, "conv_wgrad: NULL tensor");
   ConvArgs P{};
   P.d = *d; P.a = *x; P.o = *dy; P.dw = dw;
   P.M = d->k; P.N = d->c * d->r * d->s; P.K = d->n * d->p * d->q;
-  const int tiles = ((P.N + BN - 1) / BN) * ((P.M + BM - 1) / BM);
-  const int target = 4 * eg_sm_count();
-  int splits = (target + tiles - 1) / tiles;
-  const int max_splits = (P.K + 4 * BK - 1) / (4 * BK);  // at least 4 chunks of work per split
-  if (splits > max_splits) splits = max_splits;
-  if (splits < 1) splits = 1;
-  int mps = (P.K + splits - 1) / splits;
-  mps = ((mps + BK - 1) / BK) * BK;
-  splits = (P.K + mps - 1) / mps;
+  int splits, mps;
+  wgrad_split(d, &splits, &mps);
+  const size_t need = splits > 1 ? (size_t)splits * P.M * P.N * sizeof(float) : 0;
+  EG_REQUIRE(need == 0 || (workspace && ws_bytes >= need), EADGAN_ERR_WORKSPACE,
+             "conv_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  P.partial = (float*)workspace;
   P.m_per_split = mps;
   dim3 grid((P.N + BN - 1) / BN, (P.M + BM - 1) / BM, splits);
   conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(P);
   EG_LAUNCH_CHECK("conv_wgrad_kernel");
+  if (splits > 1) {
+    const int64_t numel = (int64_t)P.M * P.N;
+    int blocks = (int)((numel + 255) / 256);
+    if (blocks > 8 * eg_sm_count()) blocks = 8 * eg_sm_count();
+    wgrad_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(P.partial, splits, numel, dw);
+    EG_LAUNCH_CHECK("wgrad_sum_kernel");
+  }
   return 0;
 }
 

@@ -180,6 +180,7 @@ struct TcParams {
   int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
   int m_tiles, n_tiles, parities;  // persistent tile space: tile = (m_tile * parities + parity) * n_tiles + n_tile
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
+  int bias_len;        // number of bias entries (n_store, or dense_C for the scatter GEMM)
   const float* sigma;  // spectral-norm sigma (device scalar) or NULL: accumulators are multiplied by 1/sigma, so the
                        // packed bf16 operand can be the UN-normalised weight_orig (cached across forwards)
 };
@@ -201,7 +202,9 @@ struct Cfg {
   static constexpr int BAR_BYTES = 256;
   static constexpr int STAT_PART_BYTES = 4 * BLOCK_N * 2 * 4;   // float [4 warps][BLOCK_N][2]
   static constexpr int STAT_ACC_BYTES = STAT_MAX_CH * 2 * 8;    // double [channels][2]
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + STAT_PART_BYTES + STAT_ACC_BYTES;
+  static constexpr int BIAS_BYTES = STAT_MAX_CH * 4;            // float [channels]: the bias vector, staged once
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + STAT_PART_BYTES + STAT_ACC_BYTES +
+                              BIAS_BYTES;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -291,7 +294,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                const TcParams P) {
   using C = Cfg<BLOCK_N, MT>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by OFFSETTING the shared array (not by integer round trip): the compiler keeps the shared address
+  // space, so every access below is LDS/STS instead of a generic LD/ST through the L1TEX path
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
@@ -300,6 +305,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   float* stat_part = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES);
   double* stat_acc = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::STAT_PART_BYTES);
+  float* bias_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + C::BAR_BYTES + C::STAT_PART_BYTES +
+                                           C::STAT_ACC_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.parities * P.m_tiles * P.n_tiles;
@@ -317,8 +324,14 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     __syncwarp();
     tmem_alloc(tmem_ptr, C::TMEM_COLS);
   }
-  if (warp >= 2 && P.want_stats) {
-    for (int i = threadIdx.x - 64; i < 2 * P.stat_channels; i += 256) stat_acc[i] = 0.0;
+  if (warp >= 2) {
+    if (P.want_stats) {
+      for (int i = threadIdx.x - 64; i < 2 * P.stat_channels; i += 256) stat_acc[i] = 0.0;
+      for (int i = threadIdx.x - 64; i < 4 * BLOCK_N * 2; i += 256) stat_part[i] = 0.f;
+    }
+    if (P.bias) {  // bias_len <= STAT_MAX_CH (checked on the host)
+      for (int i = threadIdx.x - 64; i < P.bias_len; i += 256) bias_s[i] = __ldg(&P.bias[i]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -466,24 +479,24 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             for (int j = 0; j < 32; ++j) v[j] *= inv_sigma;
           }
           if (P.bias) {
-            if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast loads
-              const float4* bp = reinterpret_cast<const float4*>(P.bias + bias_base + c0);
+            if (n_left >= 32 || P.dense_C > 0) {  // 32 consecutive channels: eight 16-byte broadcast LDS
+              const float4* bp = reinterpret_cast<const float4*>(bias_s + bias_base + c0);
 #pragma unroll
               for (int g = 0; g < 8; ++g) {
-                const float4 b4 = __ldg(bp + g);
+                const float4 b4 = bp[g];
                 v[g * 4 + 0] += b4.x; v[g * 4 + 1] += b4.y; v[g * 4 + 2] += b4.z; v[g * 4 + 3] += b4.w;
               }
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j)
-                if (j < n_left) v[j] += __ldg(&P.bias[bias_base + c0 + j]);
+                if (j < n_left) v[j] += bias_s[bias_base + c0 + j];
             }
           }
           if (P.want_stats == 1) {  // BatchNorm statistics of the pre-activation output
             float o1, o2;
             warp_col_sums<true>(v, valid, lane, o1, o2);
-            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
-            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = o2;
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] += o1;   // entry owned by this warp alone
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] += o2;
           }
           if (live) {
             // the activation kind is uniform for the launch: branch ONCE, outside the element loops
@@ -528,8 +541,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (P.want_stats == 2) {  // per-channel sums of the FINAL value (bias gradient of the layer below)
             float o1, o2;
             warp_col_sums<false>(v, live, lane, o1, o2);
-            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] = o1;
-            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 1] = 0.f;
+            stat_part[(quad * BLOCK_N + c0 + lane) * 2 + 0] += o1;
           }
           if (live) {
             if (f32_out) {
@@ -558,21 +570,30 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             }
           }
         }
-        if (P.want_stats) {
-          // fold the four quadrants' partials of this sub-tile into the CTA's running per-channel totals
-          // (thread et owns channel bias_base + et [+ 256 ...]: no conflicts, no atomics)
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          for (int ch = et; ch < BLOCK_N; ch += 256) {
-            const int gch = bias_base + ch;
-            if (gch < P.stat_channels) {
+        if (P.want_stats && h == MT - 1) {
+          // Each warp keeps fp32 running column sums of ITS rows / chunks in stat_part (no sharing, no barrier).
+          // They are folded into the CTA's fp64 per-channel totals only when the next tile of this CTA covers a
+          // different channel block (or there is no next tile): thread et owns channel bias_base + et [+ 256 ...]
+          const int nt = tile + gridDim.x;
+          const bool fold = nt >= total_tiles || (nt % P.n_tiles) != (tile % P.n_tiles) ||
+                            (P.dense_C > 0);
+          if (fold) {
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int ch = et; ch < BLOCK_N; ch += 256) {
+              const int gch = bias_base + ch;
               float a = 0.f, b2 = 0.f;
 #pragma unroll
-              for (int w = 0; w < 4; ++w) { a += stat_part[(w * BLOCK_N + ch) * 2]; b2 += stat_part[(w * BLOCK_N + ch) * 2 + 1]; }
-              stat_acc[gch * 2 + 0] += (double)a;
-              stat_acc[gch * 2 + 1] += (double)b2;
+              for (int w = 0; w < 4; ++w) {
+                a += stat_part[(w * BLOCK_N + ch) * 2]; b2 += stat_part[(w * BLOCK_N + ch) * 2 + 1];
+                stat_part[(w * BLOCK_N + ch) * 2] = 0.f; stat_part[(w * BLOCK_N + ch) * 2 + 1] = 0.f;
+              }
+              if (gch < P.stat_channels) {
+                stat_acc[gch * 2 + 0] += (double)a;
+                stat_acc[gch * 2 + 1] += (double)b2;
+              }
             }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
           }
-          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
       }  // sub-tile h
     }
@@ -624,7 +645,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
                 const WgParams P) {
   using C = WgCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // align by OFFSETTING the shared array (not by integer round trip): the compiler keeps the shared address
+  // space, so every access below is LDS/STS instead of a generic LD/ST through the L1TEX path
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
   uint64_t* tmem_full_bar = empty_bar + C::STAGES;
@@ -928,6 +951,9 @@ int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, TcParams
   int mt = (bn <= 128 && (int64_t)m_tiles * parities * (n_total / bn) >= 4 * eg_sm_count()) ? 2 : 1;
   if (const char* e = getenv("EADGAN_TC_MT")) { if (bn <= 128 && atoi(e) >= 1 && atoi(e) <= 2) mt = atoi(e); }
   P.m_tiles = (m_tiles + mt - 1) / mt; P.n_tiles = n_total / bn; P.parities = parities;
+  P.bias_len = P.bias ? (P.dense_C > 0 ? P.dense_C : P.n_store) : 0;
+  EG_REQUIRE(P.bias_len <= STAT_MAX_CH, EADGAN_ERR_UNSUPPORTED, "tc conv: fused bias supports at most %d channels (got %d)",
+             STAT_MAX_CH, P.bias_len);
   EG_REQUIRE(!P.want_stats || (P.stat_channels > 0 && P.stat_channels <= STAT_MAX_CH), EADGAN_ERR_UNSUPPORTED,
              "tc conv: fused statistics support at most %d channels (got %d)", STAT_MAX_CH, P.stat_channels);
   switch (bn * 10 + mt) {

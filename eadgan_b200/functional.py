@@ -70,6 +70,24 @@ def channel_sum(t):
 # ----------------------------------------------------------------------------------
 # convolution family (fp32 SIMT path)
 # ----------------------------------------------------------------------------------
+_ws_cache = {}
+
+
+def conv_wgrad(d, x_t4, dy_t4, dw):
+    """dw (overwritten) = SIMT weight gradient; split partials go through a per-(device, stream) workspace owned
+    here (the library allocates nothing) and are summed in a fixed order: deterministic."""
+    need = L.lib().eadgan_conv_wgrad_workspace(C.byref(d))
+    ws = None
+    if need:
+        key = (dw.device, torch.cuda.current_stream().cuda_stream)
+        ws = _ws_cache.get(key)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, device=dw.device, dtype=torch.uint8)
+            _ws_cache[key] = ws
+    call("eadgan_conv_wgrad", C.byref(d), C.byref(x_t4), C.byref(dy_t4), ptr(dw), ptr(ws),
+         C.c_size_t(need), stream())
+
+
 class _ConvFn(torch.autograd.Function):
     """y = act(conv2d(x, w, b)); nn.Linear is the 1x1 case on [N,C] tensors."""
 
@@ -111,9 +129,8 @@ class _ConvFn(torch.autograd.Function):
             call("eadgan_conv_dgrad", C.byref(d), C.byref(dzd), ptr(w), None, ACT_NONE, 0.0,
                  C.byref(dxd), None, ACT_NONE, 0.0, stream())
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
-            xd = t4(x)
-            call("eadgan_conv_wgrad", C.byref(d), C.byref(xd), C.byref(dzd), ptr(dw), stream())
+            dw = torch.empty_like(w)
+            conv_wgrad(d, t4(x), dzd, dw)
         if has_b and ctx.needs_input_grad[2]:
             db = channel_sum(dz)
         return dx, dw, db, None, None, None, None
@@ -157,10 +174,10 @@ class _ConvTFn(torch.autograd.Function):
             call("eadgan_conv_fprop", C.byref(d), C.byref(dzd), ptr(w), None, ACT_NONE, 0.0,
                  C.byref(dxd), None, ACT_NONE, 0.0, stream())
         if ctx.needs_input_grad[1]:
-            dw = torch.zeros_like(w)
+            dw = torch.empty_like(w)
             xd = t4(x)
             # conv view: "x" is the big map (dz), "dy" is the small map (module input)
-            call("eadgan_conv_wgrad", C.byref(d), C.byref(dzd), C.byref(xd), ptr(dw), stream())
+            conv_wgrad(d, dzd, xd, dw)
         if has_b and ctx.needs_input_grad[2]:
             db = channel_sum(dz)
         return dx, dw, db, None, None, None, None

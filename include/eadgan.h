@@ -95,9 +95,12 @@ int eadgan_conv_fprop(const eadgan_conv_desc* d, const eadgan_tensor4* x, const 
 int eadgan_conv_dgrad(const eadgan_conv_desc* d, const eadgan_tensor4* dy, const float* w,
                       const float* bias, int act, float slope, const eadgan_tensor4* dx,
                       const eadgan_tensor4* mask, int mask_act, float mask_slope, void* stream);
-/* dw[k,c,r,s] (+)= sum_{n,p,q} dy * patch(x); dw must be zeroed by the caller unless accumulate */
+/* dw[k,c,r,s] = sum_{n,p,q} dy * patch(x)  (overwrites dw).  The reduction is split over CTAs; each split
+ * writes its own slab of the caller's workspace and the slabs are summed in a fixed order, so the result is
+ * run-to-run deterministic (no floating-point atomics).  eadgan_conv_wgrad_workspace() = bytes required. */
+size_t eadgan_conv_wgrad_workspace(const eadgan_conv_desc* d);
 int eadgan_conv_wgrad(const eadgan_conv_desc* d, const eadgan_tensor4* x, const eadgan_tensor4* dy,
-                      float* dw, void* stream);
+                      float* dw, void* workspace, size_t ws_bytes, void* stream);
 /* out[ch] = sum over n,h,w of t[n,ch,h,w]   (bias gradients) */
 int eadgan_channel_sum(const eadgan_tensor4* t, int n, int c, int h, int w, float* out,
                        void* stream);

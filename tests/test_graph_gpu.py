@@ -28,10 +28,9 @@ def test_graphed_step_matches_eager(cuda, prec):
     for i in range(1, K + 1):
         le = {k: float(v) for k, v in eager(*batch(i)).items()}
         lg = {k: float(v) for k, v in gs(*batch(i)).items()}
-        # bf16 path: every kernel is run-to-run deterministic (no float atomics), so replay == eager to the bit.
-        # fp32 SIMT path: its wgrad accumulates split partials with fp32 atomics (1e-7 summation-order noise,
-        # amplified by Adam's lr*sign(g)), so only closeness can be asserted there.
-        tol = 1e-6 if prec == "bf16" else 2e-2
+        # both paths are run-to-run deterministic up to the fp64 atomics of the BatchNorm sums (1e-16 relative):
+        # the tcgen05 kernels use no float atomics, and the SIMT wgrad sums its split partials in a fixed order
+        tol = 1e-6 if prec == "bf16" else 1e-4
         for k in le:
             assert abs(le[k] - lg[k]) <= tol * max(1.0, abs(le[k])), (i, k, le, lg)
     # weights after W + K optimiser steps: identical up to Adam's lr*sign(g) noise on elements whose gradient

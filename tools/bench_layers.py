@@ -1,5 +1,6 @@
 """GPU micro-benchmark of the tcgen05 conv entry points on the CelebA layer geometries (CUDA events,
-L2 flushed by the working set itself at B >= 512).  usage: bench_layers.py [B] [filter] [reps]"""
+L2 flushed by the working set itself at B >= 512).  usage: bench_layers.py [B] [filter] [reps] [c]
+(filter: substring of the case name, "=name" for an exact match; c: only the layer with that channel count)"""
 import os
 import sys
 
@@ -14,6 +15,7 @@ dev = torch.device("cuda:0")
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 flt = sys.argv[2] if len(sys.argv) > 2 else ""
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 10
+only_c = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 LAYERS = [(32, 64, 128), (128, 32, 256), (256, 16, 512), (512, 8, 1024)]  # (c, h, k) conv view
 
 
@@ -31,6 +33,8 @@ def timeit(fn):
 
 
 for c, h, k in LAYERS:
+    if only_c and c != only_c:
+        continue
     flops = 2.0 * B * (h // 2) ** 2 * k * c * 16
     xp = tc.alloc_padded(B, h, h, c, dev)
     tc.interior(xp).normal_()
@@ -55,11 +59,13 @@ for c, h, k in LAYERS:
         "wgrad": lambda: tc.wgrad(xp, yp),
     }
     for name, fn in cases.items():
-        if flt and flt not in name:
+        if flt and (name != flt[1:] if flt.startswith("=") else flt not in name):
             continue
         ms = timeit(fn)
         print(f"B={B} c={c:4d} h={h:3d} k={k:4d} {name:18s} {ms:8.4f} ms  {flops / ms / 1e9:8.1f} TF/s", flush=True)
 
+if only_c:
+    sys.exit(0)
 # calibration of this box: cuBLAS bf16 8192^3 (the MEASURED_PEAKS.json denominator), same process
 a = torch.randn(8192, 8192, device=dev).bfloat16(); b = torch.randn(8192, 8192, device=dev).bfloat16()
 print(f"calibration: torch.matmul bf16 8192^3 {2.0 * 8192 ** 3 / timeit(lambda: torch.matmul(a, b)) / 1e9:8.1f} TF/s")
