@@ -64,6 +64,11 @@ _PROTOS = {
     "eadgan_tc_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
     "eadgan_tc_wgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, C.c_size_t, _P],
     "eadgan_tc_gemm": [_P, _P, _P, _I, _I, _I, _P],
+    "eadgan_tc_thin_expand": [_T4, _T4, _I, _F, _I, _I, _I, _I, _P, _P],
+    "eadgan_tc_thin_pack_w": [_P, _I, _I, _I, _P, _P],
+    "eadgan_tc_thin_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
+    "eadgan_tc_thin_wgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, C.c_size_t, _P],
+    "eadgan_tc_thin_dgrad": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P],
     "eadgan_copy4": [_T4, _T4, _I, _I, _I, _I, _P],
     "eadgan_bn_stats": [_T4, _I, _I, _I, _I, _P, _P],
     "eadgan_bn_finalize": [_P, _D, _I, _F, _F, _P, _P, _P, _P, _P],
@@ -102,6 +107,8 @@ _SPECIAL = {
     "eadgan_kernel_launches": ([], C.c_int64),
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
     "eadgan_conv_wgrad_workspace": ([C.POINTER(ConvDesc)], C.c_size_t),
+    "eadgan_tc_thin_buffer_elems": ([_I, _I, _I], C.c_size_t),
+    "eadgan_tc_thin_wgrad_workspace": ([C.POINTER(TcDesc)], C.c_size_t),
     "eadgan_tc_dense_wgrad_workspace": ([_I, _I], C.c_size_t),
     "eadgan_spectral_norm_scratch_floats": ([_I, _I, _I], C.c_size_t),
 }

@@ -185,6 +185,19 @@ def _tc_ok(d, direction):
     return (d.k % 128 == 0 or d.k == 64) and d.q <= 64  # wgrad
 
 
+def _thin_ok(d, direction):
+    """the "thin" kernels: k4 s2 p1 with a 1..4-channel big map (the image)"""
+    if not (d.r == 4 and d.stride == 2 and d.pad == 1 and d.h == 2 * d.p and d.w == 2 * d.q and d.c <= 4):
+        return False
+    if not (_pow2(d.p) and _pow2(d.q)):
+        return False
+    if direction == "fprop":
+        return d.k % 32 == 0 and d.q <= 128
+    if direction == "dgrad":      # GEMM + col2im epilogue: 32-wide small map, <= 3 image channels
+        return d.k % 64 == 0 and d.q == 32 and d.c <= 3
+    return (d.k % 128 == 0 or d.k == 64) and d.q <= 64  # wgrad
+
+
 def _impl(st, d, last):
     """which kernel family runs the forward of this stage."""
     unit = d.r == 4 and d.stride == 1 and d.pad == 0 and d.h == 4 and d.w == 4 and d.p == 1 and d.q == 1
@@ -195,6 +208,8 @@ def _impl(st, d, last):
         if st.kind == "conv" and d.k <= 32 and last:
             return "dense_C"
     direction = "fprop" if st.kind == "conv" else "dgrad"
+    if _thin_ok(d, direction) and (st.kind == "conv" or (last and st.bn is None)):
+        return "thin"      # big map = the 1..4-channel image: row-expanded buffer, K = 64 (csrc/tc_conv.cu, "thin")
     if _tc_ok(d, direction):
         if _calloc(d) != d.c and st.kind == "convT" and not (last and st.bn is None):
             return "simt"  # zero-padded OUTPUT channels are only supported for an fp32 NCHW result
@@ -248,7 +263,25 @@ class _ChainFn(torch.autograd.Function):
                     return tc.pack_w_cached(_src[0], direction, ca), _src[1]
                 return tc.pack_w(_wc, None, direction, ca), None
             rec["packed"] = packed
-            if impl == "dense_T":      # 1x1 -> 4x4 ConvTranspose: batch GEMM, scatter epilogue
+
+            def packed_thin(direction, _src=src, _wc=wc):
+                if _src is not None:
+                    return tc.thin_pack_w_cached(_src[0], direction), _src[1]
+                return tc.thin_pack_w(_wc, direction), None
+            rec["packed_thin"] = packed_thin
+            if impl == "thin" and st.kind == "conv":
+                inp = cur
+                r = tc.thin_expand(cur.view())
+                rec["R"] = r
+                wpk, sg = packed_thin("fprop")
+                if last:
+                    raise RuntimeError("eadgan_b200.chain: a thin conv cannot be the last stage")
+                out = _Buf(tc.thin_fprop(r, wpk, b, d.c, cout, epi_act[0], epi_act[1], stats=stats, sigma=sg), "pad")
+            elif impl == "thin":       # ConvTranspose onto the image: GEMM over input pixels + col2im epilogue
+                inp = _Buf(cur.padded(), "pad")
+                wpk, sg = packed_thin("dgrad")
+                out = _Buf(tc.thin_dgrad(inp.t, wpk, b, d.c, epi_act[0], epi_act[1], sigma=sg), "ext")
+            elif impl == "dense_T":      # 1x1 -> 4x4 ConvTranspose: batch GEMM, scatter epilogue
                 a = tc.pad_rows(cur.t.reshape(d.n, d.k), _r64(d.k))
                 out = _Buf(tc.dense_scatter(a, tc.dense_pack(wc, _r64(d.k), False), b, d.c), "pad")
                 inp = cur
@@ -379,7 +412,31 @@ class _ChainFn(torch.autograd.Function):
             sums_buf = torch.zeros(in_shape[1], device=dev, dtype=torch.float64) if want_sums else None
             sums_used = False
             # ---- 2./3. weight gradient and input gradient -----------------------------------------
-            if impl == "dense_T":
+            if impl == "thin":
+                if st.kind == "conv":      # big map = stage input (image), small map = dz
+                    r = sv["R"]
+                    if _thin_ok(d, "wgrad"):
+                        dw = tc.thin_wgrad(r, dz.padded(), d.c)
+                    else:
+                        dw = torch.empty_like(sv["w"])
+                        Fn.conv_wgrad(d, t4(sv["inp"].view()), t4(dz.view()), dw)
+                    if need_dx and si == 0 and _thin_ok(d, "dgrad"):
+                        wpk, sg = sv["packed_thin"]("dgrad")
+                        dx = _Buf(tc.thin_dgrad(dz.padded(), wpk, None, d.c, sigma=sg), "ext")
+                else:                      # big map = dz (image gradient), small map = stage input
+                    r = tc.thin_expand(dz.view())
+                    if _thin_ok(d, "wgrad"):
+                        dw = tc.thin_wgrad(r, sv["inp"].t, d.c)
+                    else:
+                        dw = torch.empty_like(sv["w"])
+                        Fn.conv_wgrad(d, t4(dz.view()), t4(sv["inp"].view()), dw)
+                    if need_dx and si > 0:
+                        wpk, sg = sv["packed_thin"]("fprop")
+                        dx = _Buf(tc.thin_fprop(r, wpk, None, d.c, in_shape[1], mask=sv["inp"].t if fuse else None,
+                                                mask_mode=mask_act, slope=mask_slope, stats=sums_buf, stats_mode=2,
+                                                sigma=sg), "pad")
+                        sums_used = want_sums
+            elif impl == "dense_T":
                 dw = tc.dense_wgrad(sv["a"], dz.padded(), d.k)
             elif impl == "dense_C":
                 a = tc.pad_rows(dz.t.reshape(d.n, d.k), 64)

@@ -180,6 +180,7 @@ struct TcParams {
   int dense_C;         // > 0: 4x4 <-> 1x1 "dense" layers; channels of the padded [n,6,6,C] map
   int m_tiles, n_tiles, parities;  // persistent tile space: tile = (m_tile * parities + parity) * n_tiles + n_tile
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
+  int thin;            // fprop on a <= 4-channel image: ONE 64-wide k block, A boxes from the row-expanded buffer
   int bias_len;        // number of bias entries (n_store, or dense_C for the scatter GEMM)
   const float* sigma;  // spectral-norm sigma (device scalar) or NULL: accumulators are multiplied by 1/sigma, so the
                        // packed bf16 operand can be the UN-normalised weight_orig (cached across forwards)
@@ -366,7 +367,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               tma_load_4d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (t & 3), 1 + (t >> 2), m_tile * BLOCK_M);
             } else {
               const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
-              if (P.mode == MODE_FPROP) {
+              if (P.mode == MODE_FPROP && P.thin) {
+                // R[n][oy][X][ky][4]: the 4x4x4 patch of output (oy, ox) is the 64 contiguous elements at X = 2 ox
+                tma_load_4d(sah, &map_a, &full_bar[stage], 0, 0, y0, b0);
+              } else if (P.mode == MODE_FPROP) {
                 const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
                 tma_load_5d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
               } else {  // t = ty*2+tx
@@ -628,6 +632,7 @@ struct WgParams {
   int Ktot;             // 16*c
   float* partial;       // [splits][k][16c]
   int dense;            // 1: "pixels" are batch rows; A boxes from a [n][Mp] matrix, B boxes from [n,6,6,C]
+  int thin;             // 1: big map is a <= 4-channel image; B = one 64-wide patch box of the row-expanded buffer
 };
 
 template <int BLOCK_N>  // BLOCK_N columns of kk per tile (multiple of 64)
@@ -698,6 +703,9 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
 #pragma unroll
           for (int h = 0; h < 2; ++h)
             tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+          if (P.thin) {
+            tma_load_4d(sb, &map_x, &full_bar[stage], 0, 0, y0, b0);
+          } else
 #pragma unroll
           for (int i = 0; i < BLOCK_N / 64; ++i) {
             const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
@@ -1260,5 +1268,403 @@ extern "C" int eadgan_tc_dense_wgrad(const void* a_bf16, const void* y_pad, floa
   if (int rc = launch_wgrad<256>(ma, mx, P, grid, st)) return rc;
   dense_wgrad_reduce_kernel<<<dim3(C / 64, m_real), 256, 0, st>>>(P.partial, mp, C, dw);
   EG_LAUNCH_CHECK("dense_wgrad_reduce_kernel");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------
+// "Thin" image layers: the k4 s2 p1 convolutions whose big map is the IMAGE (1..4 channels) --
+// D's first Conv2d(3,128) (celebA/EAD-GAN_celebA.py:110), G's last ConvTranspose2d(128,3) (:90), the
+// dSprites trunks' Conv2d(1|3,32) (dSprites/rp.py:66,95,165) and G's ConvTranspose2d(64,1|3) (:141).
+// Padding 3 channels to 32 made these layers stream 8x the bytes they need; here
+//   * the image lives in a ROW-EXPANDED bf16 buffer R[n][p][W+2][ky 4][c 4]: R[n][oy][X][ky][c] =
+//     Xpad[n][2 oy + ky][X][c].  The whole 4x4x(4) patch of output pixel (oy, ox) is then the 64
+//     CONTIGUOUS elements starting at X = 2 ox, so one TMA box (64 elems, q pixels at a 64-byte stride,
+//     rows, images) is a ready 128-byte-swizzled K-major operand with K = 64 = (kx, ky, c);
+//   * Conv2d forward / ConvTranspose2d input-gradient: ONE k block per 128-pixel tile (thin fprop);
+//   * weight gradient: dw[ko][kk] = sum_pixels dy[pix][ko] R_patch[pix][kk], N = 64 (thin wgrad);
+//   * ConvTranspose2d forward / Conv2d input-gradient: Z[pixel][(ky,kx,c)] = y[pixel][:] . W, N = 64,
+//     K = k, followed by the col2im overlap-add IN THE EPILOGUE (shuffles along x, shared memory along y):
+//     the small map is read once instead of once per output parity and tap.
+// ------------------------------------------------------------------------------------
+namespace {
+
+// fp32 image (any strides) [* act'(mask)]  ->  R[n][p][W+2][4][4] bf16 (zero halo, zero padding channels)
+__global__ void __launch_bounds__(256) thin_expand_kernel(eadgan_tensor4 src, eadgan_tensor4 mask, int act, float slope,
+                                                          int n, int c_real, int h, int w,
+                                                          __nv_bfloat16* __restrict__ R) {
+  const int p = h / 2, wp = w + 2;
+  const int64_t total = (int64_t)n * p * wp * 4;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ky = (int)(i & 3);
+    int64_t r = i >> 2;
+    const int X = (int)(r % wp); r /= wp;
+    const int oy = (int)(r % p);
+    const int b = (int)(r / p);
+    const int y = 2 * oy + ky - 1, x = X - 1;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (y >= 0 && y < h && x >= 0 && x < w) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < c_real) {
+          v[c] = eg_ld(src.ptr, (int64_t)b * src.sn + (int64_t)c * src.sc + (int64_t)y * src.sh + (int64_t)x * src.sw,
+                       src.dtype);
+          if (act != EADGAN_ACT_NONE)
+            v[c] *= eg_act_grad(eg_ld(mask.ptr, (int64_t)b * mask.sn + (int64_t)c * mask.sc + (int64_t)y * mask.sh +
+                                                    (int64_t)x * mask.sw, mask.dtype), act, slope);
+        }
+      }
+    }
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&lo);
+    pk.y = *reinterpret_cast<uint32_t*>(&hi);
+    *reinterpret_cast<uint2*>(R + i * 4) = pk;
+  }
+}
+
+// direction 0: Wf[ko][kx*16 + ky*4 + c] = w[ko][c][ky][kx]           (bf16 [k][64])      thin fprop B operand
+// direction 1: Wt[ky*16 + kx*4 + c][ki] = w[ki][c][ky][kx]           (bf16 [64][k])      thin dgrad B operand
+__global__ void thin_pack_kernel(const float* __restrict__ w, int k, int c_real, int direction,
+                                 __nv_bfloat16* __restrict__ out) {
+  const int total = k * 64;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    int ko, ky, kx, c;
+    if (direction == 0) { ko = i >> 6; const int kk = i & 63; kx = kk >> 4; ky = (kk >> 2) & 3; c = kk & 3; }
+    else { const int row = i / k; ko = i - row * k; ky = row >> 4; kx = (row >> 2) & 3; c = row & 3; }
+    out[i] = __float2bfloat16_rn(c < c_real ? w[(((int64_t)ko * c_real + c) * 4 + ky) * 4 + kx] : 0.f);
+  }
+}
+
+// thin wgrad: sum split partials [splits][k_pad][64] (column kx*16+ky*4+c) -> dw[ko][c][ky][kx]
+__global__ void thin_wgrad_reduce_kernel(const float* __restrict__ partial, int splits, int k_pad, int k, int c_real,
+                                         float* __restrict__ dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= k * 64) return;
+  const int ko = i >> 6, kk = i & 63;
+  const int kx = kk >> 4, ky = (kk >> 2) & 3, c = kk & 3;
+  if (c >= c_real) return;
+  float s = 0.f;
+  for (int sp = 0; sp < splits; ++sp) s += partial[((int64_t)sp * k_pad + ko) * 64 + kk];
+  dw[(((int64_t)ko * c_real + c) * 4 + ky) * 4 + kx] = s;
+}
+
+// 4-D view of the row-expanded image buffer: (64-element window, ox at a 32-element stride, oy, n)
+int map_thin(CUtensorMap* m, const void* base, int n, int h, int w, int Tw, int Th, int Tb) {
+  const int p = h / 2, q = w / 2;
+  const uint64_t row = (uint64_t)(w + 2) * 16;   // elements per (n, oy) row of R
+  const uint64_t dims[4] = {64, (uint64_t)q, (uint64_t)p, (uint64_t)n};
+  const uint64_t st[3] = {64, row * 2, row * 2 * p};
+  const uint32_t box[4] = {64, (uint32_t)Tw, (uint32_t)Th, (uint32_t)Tb};
+  return encode_map(m, base, 4, dims, st, box);
+}
+
+struct ThinDgParams {
+  int n, p;               // images, small-map rows (q == 32)
+  int nkb;                // k / 64
+  int tiles_per_img;      // p / 2: a tile is rows [r0-1, r0+2] of one image and OWNS rows r0, r0+1
+  int c_real;
+  int act; float slope;
+  const float* bias;      // [c_real] or NULL
+  const float* sigma;
+  float* out;             // fp32 NCHW [n][c_real][2p][64]
+};
+
+constexpr int THIN_STAGES = 6;
+constexpr int THIN_STAGE_BYTES = A_BYTES + 64 * BLOCK_K * 2;   // 16 KB + 8 KB
+constexpr int THIN_SMEM = THIN_STAGES * THIN_STAGE_BYTES + 1024 + 256 + 2 * 4 * 12 * 32 * 4;
+
+// Z[128 pixels][64] = y_tile[128][k] . Wt^T, then col2im.  192 threads: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// (TMEM lane quadrant q = warp & 3 = tile row q; lane = x).  Input row m owns output rows 2m, 2m+1:
+//   out[2m  ][2j+b] = Xr_m[ky 1][b] + Xr_{m-1}[ky 3][b]        Xr[ky][0] = Z[ky][kx 1] + Z_{j-1}[ky][kx 3]
+//   out[2m+1][2j+b] = Xr_m[ky 2][b] + Xr_{m+1}[ky 0][b]        Xr[ky][1] = Z[ky][kx 2] + Z_{j+1}[ky][kx 0]
+__global__ void __launch_bounds__(192, 1)
+tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const ThinDgParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + THIN_STAGES * THIN_STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + THIN_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + THIN_STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* xs = reinterpret_cast<float*>(smem + THIN_STAGES * THIN_STAGE_BYTES + 256);  // [2 buf][4 rows][12][32]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = P.n * P.tiles_per_img;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < THIN_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 128);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int b = tile / P.tiles_per_img, r0 = (tile % P.tiles_per_img) * 2;
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * THIN_STAGE_BYTES;
+          mbar_expect_tx(&full_bar[stage], THIN_STAGE_BYTES);
+          // padded small map rows r0 .. r0+3  =  image rows r0-1 .. r0+2 (row -1 / row p are the zero halo)
+          tma_load_4d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, 1, r0, b);
+          tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BLOCK_K, 0);
+          if (++stage == THIN_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(BLOCK_M, 64, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 64);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * THIN_STAGE_BYTES);
+          const uint32_t sb = sa + A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)
+            umma_bf16(d_tmem, make_desc(sa + k * 32, 16, 1024), make_desc(sb + k * 32, 16, 1024), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == P.nkb - 1) umma_commit(&tmem_full_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == THIN_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int quad = warp & 3;   // tile row: 0 = r0-1 (halo), 1 = r0, 2 = r0+1, 3 = r0+2 (halo)
+    const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (P.bias) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) if (c < P.c_real) bias[c] = __ldg(&P.bias[c]);
+    }
+    const int OW = 64, OH = 2 * P.p;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int b = tile / P.tiles_per_img, r0 = (tile % P.tiles_per_img) * 2;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      float z[64];   // z[ky*16 + kx*4 + c]
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 64) + ((uint32_t)(quad * 32) << 16);
+      tmem_ld32(acc, z);
+      tmem_ld32(acc + 32, z + 32);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+      // ---- x direction (neighbouring lanes); edges of the 32-wide map contribute zero ----
+      float xr[4][2][3];
+#pragma unroll
+      for (int ky = 0; ky < 4; ++ky) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float left = __shfl_up_sync(0xffffffffu, z[ky * 16 + 3 * 4 + c], 1);
+          float right = __shfl_down_sync(0xffffffffu, z[ky * 16 + 0 * 4 + c], 1);
+          if (lane == 0) left = 0.f;
+          if (lane == 31) right = 0.f;
+          xr[ky][0][c] = z[ky * 16 + 1 * 4 + c] + left;
+          xr[ky][1][c] = z[ky * 16 + 2 * 4 + c] + right;
+        }
+      }
+      // ---- y direction (neighbouring warps) through shared memory ----
+      float* mine = xs + ((buf * 4 + quad) * 12) * 32;
+#pragma unroll
+      for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          mine[(0 * 6 + bb * 3 + c) * 32 + lane] = xr[0][bb][c];   // what the row ABOVE needs (its out[2m+1])
+          mine[(1 * 6 + bb * 3 + c) * 32 + lane] = xr[3][bb][c];   // what the row BELOW needs (its out[2m])
+        }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (quad == 1 || quad == 2) {
+        const int m = r0 + quad - 1;
+        const float* above = xs + ((buf * 4 + quad - 1) * 12) * 32;   // row m-1: its ky = 3 sums
+        const float* below = xs + ((buf * 4 + quad + 1) * 12) * 32;   // row m+1: its ky = 0 sums
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c < P.c_real) {
+            float o[2][2];
+#pragma unroll
+            for (int bb = 0; bb < 2; ++bb) {
+              o[0][bb] = (xr[1][bb][c] + above[(1 * 6 + bb * 3 + c) * 32 + lane]) * inv_sigma + bias[c];
+              o[1][bb] = (xr[2][bb][c] + below[(0 * 6 + bb * 3 + c) * 32 + lane]) * inv_sigma + bias[c];
+            }
+            if (P.act != EADGAN_ACT_NONE) {
+#pragma unroll
+              for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) o[a][bb] = eg_act(o[a][bb], P.act, P.slope);
+            }
+            float* op = P.out + (((int64_t)b * P.c_real + c) * OH + 2 * m) * OW + 2 * lane;
+            *reinterpret_cast<float2*>(op) = make_float2(o[0][0], o[0][1]);
+            *reinterpret_cast<float2*>(op + OW) = make_float2(o[1][0], o[1][1]);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+int check_thin(const eadgan_tc_desc* d, const char* who) {
+  if (int e = check_tc(d, who)) return e;
+  EG_REQUIRE(d->c >= 1 && d->c <= 4, EADGAN_ERR_UNSUPPORTED, "%s: the image must have 1..4 channels (got %d)", who, d->c);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" size_t eadgan_tc_thin_buffer_elems(int n, int h, int w) { return (size_t)n * (h / 2) * (w + 2) * 16; }
+
+extern "C" int eadgan_tc_thin_expand(const eadgan_tensor4* src, const eadgan_tensor4* mask, int act, float slope, int n,
+                                     int c_real, int h, int w, void* r_out, void* stream) {
+  EG_REQUIRE(src && src->ptr && r_out && n > 0 && c_real >= 1 && c_real <= 4 && h >= 2 && w >= 2 && h % 2 == 0 &&
+                 w % 2 == 0, EADGAN_ERR_INVALID, "tc_thin_expand: bad arguments");
+  EG_REQUIRE(act == EADGAN_ACT_NONE || (mask && mask->ptr), EADGAN_ERR_INVALID, "tc_thin_expand: act without mask");
+  const int64_t total = (int64_t)n * (h / 2) * (w + 2) * 4;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 32 * eg_sm_count()) blocks = 32 * eg_sm_count();
+  eadgan_tensor4 mk = mask ? *mask : *src;
+  thin_expand_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(*src, mk, mask ? act : EADGAN_ACT_NONE, slope, n, c_real, h,
+                                                               w, (__nv_bfloat16*)r_out);
+  EG_LAUNCH_CHECK("thin_expand_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_tc_thin_pack_w(const float* w, int k, int c_real, int direction, void* out, void* stream) {
+  EG_REQUIRE(w && out && k > 0 && c_real >= 1 && c_real <= 4 && (direction == 0 || direction == 1), EADGAN_ERR_INVALID,
+             "tc_thin_pack_w: bad arguments");
+  thin_pack_kernel<<<(k * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(w, k, c_real, direction, (__nv_bfloat16*)out);
+  EG_LAUNCH_CHECK("thin_pack_kernel");
+  return 0;
+}
+
+// y[n,p+2,q+2,k] (padded NHWC bf16) or fp32 NCHW = act(conv(image, W / sigma) + bias) [* mask'(.)]
+extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, const void* w_packed, const float* bias,
+                                    void* y, const void* mask, double* stats, const float* sigma, void* stream) {
+  if (int e = check_thin(d, "tc_thin_fprop")) return e;
+  EG_REQUIRE(r_buf && w_packed && y, EADGAN_ERR_INVALID, "tc_thin_fprop: NULL pointer");
+  const int p = d->h / 2, q = d->w / 2;
+  TcParams P{};
+  P.mode = MODE_FPROP; P.thin = 1; P.n = d->n; P.p = p; P.q = q;
+  EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_thin_fprop: output map %dx%d must be a power of two <= 128 wide", p, q);
+  const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
+  const int bn = pick_bn(d->k);
+  EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_fprop: k=%d must be a multiple of 32", d->k);
+  P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = 4; P.qblocks = 1; P.nkb = 1;
+  P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
+  P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
+  P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k; P.stat_channels = d->k; P.sigma = sigma;
+  EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_thin_fprop: mask_mode without mask");
+  EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_thin_fprop: want_stats without stats");
+  CUtensorMap ma, mb;
+  if (int e = map_thin(&ma, r_buf, d->n, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
+  if (int e = map_matrix(&mb, w_packed, d->k, 64, bn)) return e;
+  return dispatch_conv(bn, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
+}
+
+namespace {
+int thin_wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* splits) {
+  const int p = d->h / 2, q = d->w / 2;
+  EG_REQUIRE(d->k % 128 == 0 || d->k == 64, EADGAN_ERR_UNSUPPORTED, "tc_thin_wgrad: k=%d must be 64 or a multiple of 128",
+             d->k);
+  P->n = d->n; P->p = p; P->q = q; P->k = d->k; P->c = 4; P->thin = 1;
+  EG_REQUIRE(pick_tile(p, q, 64, &P->Tw, &P->Th, &P->Tb) == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_thin_wgrad: small map %dx%d must be a power of two <= 64 wide", p, q);
+  P->tiles_y = p / P->Th; P->qblocks = 1; P->Ktot = 64;
+  P->steps_total = ((d->n + P->Tb - 1) / P->Tb) * P->tiles_y;
+  // the only parallelism is the split of the pixel reduction: one CTA per SM (per 128-row ko tile)
+  const int ko_tiles = (d->k + 127) / 128;
+  int s = eg_sm_count() / ko_tiles;
+  const int max_s = (P->steps_total + 7) / 8;
+  if (s > max_s) s = max_s;
+  if (s < 1) s = 1;
+  P->steps_per_split = (P->steps_total + s - 1) / s;
+  *splits = (P->steps_total + P->steps_per_split - 1) / P->steps_per_split;
+  return 0;
+}
+}  // namespace
+
+extern "C" size_t eadgan_tc_thin_wgrad_workspace(const eadgan_tc_desc* d) {
+  if (!d) return 0;
+  WgParams P{};
+  int splits = 0;
+  if (thin_wgrad_plan(d, &P, &splits) != 0) return 0;
+  return (size_t)splits * (((d->k + 127) / 128) * 128) * 64 * sizeof(float);
+}
+
+// dw[k][c][4][4] fp32 = sum over pixels of dy (padded NHWC bf16 small map) x image patch (row-expanded buffer)
+extern "C" int eadgan_tc_thin_wgrad(const eadgan_tc_desc* d, const void* r_buf, const void* dy_pad, float* dw,
+                                    void* workspace, size_t ws_bytes, void* stream) {
+  if (int e = check_thin(d, "tc_thin_wgrad")) return e;
+  EG_REQUIRE(r_buf && dy_pad && dw && workspace, EADGAN_ERR_INVALID, "tc_thin_wgrad: NULL pointer");
+  WgParams P{};
+  int splits = 0;
+  if (int e = thin_wgrad_plan(d, &P, &splits)) return e;
+  const int k_pad = ((d->k + 127) / 128) * 128;
+  const size_t need = (size_t)splits * k_pad * 64 * sizeof(float);
+  EG_REQUIRE(ws_bytes >= need, EADGAN_ERR_WORKSPACE, "tc_thin_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
+  P.partial = (float*)workspace;
+  WgParams PK = P;
+  PK.k = k_pad;
+  CUtensorMap mdy, mx;
+  if (int e = map_small(&mdy, dy_pad, d->n, d->k, P.p, P.q, P.Tw, P.Th, P.Tb)) return e;
+  if (int e = map_thin(&mx, r_buf, d->n, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = launch_wgrad<64>(mdy, mx, PK, dim3(1, k_pad / 128, splits), st)) return rc;
+  thin_wgrad_reduce_kernel<<<(d->k * 64 + 255) / 256, 256, 0, st>>>(P.partial, splits, k_pad, d->k, d->c, dw);
+  EG_LAUNCH_CHECK("thin_wgrad_reduce_kernel");
+  return 0;
+}
+
+// out fp32 NCHW [n][c][2p][64] = act(conv_transpose(dy, W / sigma) + bias): GEMM over input pixels + col2im epilogue
+extern "C" int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed, const float* bias,
+                                    float* out, const float* sigma, void* stream) {
+  if (int e = check_thin(d, "tc_thin_dgrad")) return e;
+  EG_REQUIRE(dy_pad && w_packed && out, EADGAN_ERR_INVALID, "tc_thin_dgrad: NULL pointer");
+  const int p = d->h / 2, q = d->w / 2;
+  EG_REQUIRE(q == 32 && p >= 2 && p % 2 == 0, EADGAN_ERR_UNSUPPORTED,
+             "tc_thin_dgrad: the small map must be 32 wide with an even number of rows (got %dx%d)", p, q);
+  EG_REQUIRE(d->k % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_dgrad: k=%d must be a multiple of 64", d->k);
+  EG_REQUIRE(d->c <= 3, EADGAN_ERR_UNSUPPORTED, "tc_thin_dgrad: at most 3 image channels");
+  ThinDgParams P{};
+  P.n = d->n; P.p = p; P.nkb = d->k / 64; P.tiles_per_img = p / 2; P.c_real = d->c; P.act = d->act; P.slope = d->slope;
+  P.bias = bias; P.sigma = sigma; P.out = out;
+  CUtensorMap ma, mb;
+  if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, 32, 4, 1)) return e;
+  if (int e = map_matrix(&mb, w_packed, 64, (uint64_t)d->k, 64)) return e;
+  static bool attr_set = false;
+  if (!attr_set) {
+    EG_CUDA(cudaFuncSetAttribute(tc_thin_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM));
+    attr_set = true;
+  }
+  const int total = d->n * (p / 2);
+  const int sms = eg_sm_count();
+  const int waves = (total + sms - 1) / sms;
+  const int grid = (total + waves - 1) / waves;
+  tc_thin_dgrad_kernel<<<grid, 192, THIN_SMEM, (cudaStream_t)stream>>>(ma, mb, P);
+  EG_LAUNCH_CHECK("tc_thin_dgrad_kernel");
   return 0;
 }

@@ -206,6 +206,78 @@ def wgrad(xp, yp, c_real=0):
     return dw
 
 
+# ---- "thin" image layers (1..4-channel big map): row-expanded image buffer R[n][h/2][w+2][4][4] bf16 ----------
+def thin_expand(x, mask_y=None, act=ACT_NONE, slope=0.0):
+    """fp32 image [n,c<=4,h,w] (any strides) [* act'(mask_y)] -> row-expanded bf16 buffer (every element written)."""
+    n, c, h, w = x.shape
+    r = torch.empty((n, h // 2, w + 2, 4, 4), device=x.device, dtype=torch.bfloat16)
+    src = t4(x)
+    mk = t4(mask_y) if mask_y is not None else None
+    call("eadgan_tc_thin_expand", C.byref(src), C.byref(mk) if mk is not None else None, int(act), float(slope), n, c, h, w,
+         ptr(r), stream())
+    return r
+
+
+def thin_pack_w(w, direction):
+    """fp32 [k, c<=4, 4, 4] -> bf16 [k][64] ("fprop") or [64][k] ("dgrad")."""
+    k, c = w.shape[0], w.shape[1]
+    assert tuple(w.shape[2:]) == (4, 4) and c <= 4
+    out = torch.empty(k * 64, device=w.device, dtype=torch.bfloat16)
+    call("eadgan_tc_thin_pack_w", ptr(w.contiguous()), k, c, 0 if direction == "fprop" else 1, ptr(out), stream())
+    return out
+
+
+def thin_pack_w_cached(param, direction):
+    key = (id(param), "thin_" + direction, None)
+    token = (param._version, param.data_ptr(), L.weights_epoch)
+    hit = _pack_cache.get(key)
+    if hit is not None and hit[0]() is param and hit[1] == token:
+        return hit[2]
+    out = thin_pack_w(param.detach(), direction)
+    if hit is None or hit[0]() is not param:
+        weakref.finalize(param, _pack_cache.pop, key, None)
+    _pack_cache[key] = (weakref.ref(param), token, out)
+    return out
+
+
+def thin_fprop(r, wpk, bias, c, k, act=ACT_NONE, slope=0.0, mask=None, mask_mode=0, stats=None, stats_mode=1, sigma=None,
+               out=None):
+    """row-expanded image r -> small map [n,p+2,q+2,k] padded NHWC bf16."""
+    n, p, wp = r.shape[0], r.shape[1], r.shape[2]
+    h, w = 2 * p, wp - 2
+    d = _desc(n, c, h, w, k, act, slope, False, stats_mode if stats is not None else 0, mask_mode)
+    if out is None:
+        out = alloc_padded(n, h // 2, w // 2, k, r.device)
+    call("eadgan_tc_thin_fprop", C.byref(d), ptr(r), ptr(wpk), ptr(bias), ptr(out), ptr(mask), ptr(stats), ptr(sigma),
+         stream())
+    return out
+
+
+def thin_wgrad(r, yp, c):
+    """dw[k,c,4,4] fp32 from the row-expanded image r and the small map yp (padded NHWC bf16)."""
+    n, p, wp = r.shape[0], r.shape[1], r.shape[2]
+    k = yp.shape[3]
+    d = _desc(n, c, 2 * p, wp - 2, k)
+    need = L.lib().eadgan_tc_thin_wgrad_workspace(C.byref(d))
+    if need == 0:
+        raise RuntimeError(f"tc thin wgrad: unsupported geometry n={n} c={c} h={2 * p} k={k}")
+    ws = _workspace(need, r.device)
+    dw = torch.empty((k, c, 4, 4), device=r.device, dtype=torch.float32)
+    call("eadgan_tc_thin_wgrad", C.byref(d), ptr(r), ptr(yp), ptr(dw), ptr(ws), C.c_size_t(ws.numel()), stream())
+    return dw
+
+
+def thin_dgrad(yp, wpk, bias, c, act=ACT_NONE, slope=0.0, sigma=None, out=None):
+    """small map yp [n,p+2,34,k] -> fp32 NCHW image [n,c,2p,64] = act(conv_transpose(yp, W/sigma) + bias)."""
+    n, pp, qp, k = yp.shape
+    h, w = 2 * (pp - 2), 2 * (qp - 2)
+    d = _desc(n, c, h, w, k, act, slope, True)
+    if out is None:
+        out = torch.empty((n, c, h, w), device=yp.device, dtype=torch.float32)
+    call("eadgan_tc_thin_dgrad", C.byref(d), ptr(yp), ptr(wpk), ptr(bias), ptr(out), ptr(sigma), stream())
+    return out
+
+
 def gemm(a, b):
     """C[m,n] fp32 = A[m,k] bf16 @ B[n,k]^T bf16 through the tcgen05 mainloop."""
     m, kk = a.shape

@@ -156,6 +156,38 @@ int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const void* dy_p
 int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f32, int m, int n, int kk,
                    void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* "Thin" image layers: k4 s2 p1 convolutions whose big map is the IMAGE       */
+/* (1..4 channels): D's first nn.Conv2d(3,128,4,2,1) (celebA/EAD-GAN_celebA.py */
+/* :110), G's last nn.ConvTranspose2d(128,3,4,2,1) (:90), the dSprites trunks'  */
+/* nn.Conv2d(1|3,32,4,2,1) (dSprites/rp.py:66,95,165; colored rp_color.py) and  */
+/* G's nn.ConvTranspose2d(64,1|3,4,2,1) (rp.py:141).  The image is held in a    */
+/* row-expanded bf16 buffer R[n][h/2][w+2][ky 4][c 4] (R[n][oy][X][ky][c] =     */
+/* Xpad[n][2 oy + ky][X][c]) so that the 4x4x4 patch of an output pixel is 64   */
+/* contiguous elements = one 128-byte K-major tcgen05 operand row (K = 64).     */
+/* desc: c = image channels (1..4), h, w = image size, k = small-map channels.  */
+/* ------------------------------------------------------------------------- */
+size_t eadgan_tc_thin_buffer_elems(int n, int h, int w);   /* bf16 elements of R */
+/* src: fp32/bf16 image tensor (any strides); mask/act: optional fused activation backward,
+ * R <- src * act'(mask) with mask the saved post-activation output (act = 0: plain copy) */
+int eadgan_tc_thin_expand(const eadgan_tensor4* src, const eadgan_tensor4* mask, int act, float slope,
+                          int n, int c_real, int h, int w, void* r_out, void* stream);
+/* fp32 [k,c,4,4] -> bf16 [k][64] (direction 0, fprop operand) or [64][k] (direction 1, dgrad operand) */
+int eadgan_tc_thin_pack_w(const float* w, int k, int c_real, int direction, void* out, void* stream);
+/* Conv2d forward / ConvTranspose2d input-gradient: y = act(conv(image, W/sigma) + bias) [* mask'] */
+int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, const void* w_packed,
+                         const float* bias, void* y, const void* mask, double* stats, const float* sigma,
+                         void* stream);
+/* weight gradient dw[k,c,4,4] fp32; deterministic (split partials summed in a fixed order) */
+size_t eadgan_tc_thin_wgrad_workspace(const eadgan_tc_desc* d);
+int eadgan_tc_thin_wgrad(const eadgan_tc_desc* d, const void* r_buf, const void* dy_pad, float* dw,
+                         void* workspace, size_t ws_bytes, void* stream);
+/* ConvTranspose2d forward / Conv2d input-gradient onto the image: fp32 NCHW [n,c,h,w] =
+ * act(conv_transpose(dy, W/sigma) + bias); one GEMM over the small map's pixels (N = 16 taps x 4),
+ * col2im overlap-add in the epilogue.  Needs a 32-wide small map and c <= 3. */
+int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed,
+                         const float* bias, float* out, const float* sigma, void* stream);
+
 /* "dense" 4x4 <-> 1x1 layers as batch GEMMs on the same tcgen05 mainloop:
  * nn.ConvTranspose2d(218,1024,4,1,0) on the 1x1 latent (celebA/EAD-GAN_celebA.py:76) and the D/Q head
  * nn.Conv2d(1024,19,4,1,0) on the 4x4 map (celebA/EAD-GAN_celebA.py:122).  The weight is always viewed
