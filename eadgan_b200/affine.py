@@ -2,10 +2,13 @@
 closed-form recovery of relative affine parameters (reference: celebA/utils_rpqxy.py:25-116,
 dSprites/utils_rp.py:23-147, dSprites/utils_pxy.py:24-126).
 
-SURVEY.md section 8(f) ranks these as "next" rows: they stay stock differentiable torch
-ops for now, but are restated here to run ENTIRELY ON THE DEVICE -- the reference builds
-``torch.eye(3)`` on the CPU and assigns CUDA slices into it, i.e. 8-9 synchronising D2H
-copies per call; this version has no host round trip.
+SURVEY.md section 8(f) ranks 1-2.  The reference builds ``torch.eye(3)`` on the CPU and assigns
+CUDA slices into it, i.e. 8-9 synchronising D2H copies per call.  Here the
+algebra is restated in closed form (``*_torch`` functions: plain differentiable torch ops, no host round
+trip; they run on any device and are what the CPU tests pin to the oracle), and on CUDA tensors the public
+functions dispatch to ONE fused kernel each (csrc/glue.cu): the relative-code recovery evaluated in
+forward-mode dual numbers with a stored Jacobian (backward = J^T g), and the spatial transformer
+(affine_grid + bilinear grid_sample) as a single forward kernel.
 """
 from __future__ import annotations
 
@@ -13,6 +16,12 @@ import math
 
 import torch
 import torch.nn.functional as TF
+
+from . import functional as Fn
+
+
+def _fused(*ts):
+    return all(t.is_cuda and t.dtype == torch.float32 for t in ts)
 
 
 def _mat3(rows):
@@ -47,6 +56,13 @@ def _rzt_parts(code5):
 
 
 def celeba_relative_code(real_code, trans_code):
+    """affine_regularzier of celebA/utils_rpqxy.py:82-116 (fused kernel on CUDA tensors)."""
+    if _fused(real_code, trans_code):
+        return Fn.relative_code(real_code, trans_code, Fn.REL_CELEBA)
+    return celeba_relative_code_torch(real_code, trans_code)
+
+
+def celeba_relative_code_torch(real_code, trans_code):
     """affine_regularzier of celebA/utils_rpqxy.py:82-116.  rel = M(trans) @ inverse(M(real)); both are
     affine (last row 0 0 1), so the inverse is written in closed form -- torch.inverse / linalg.inv check
     for singularity on the HOST (a device->host sync in the middle of every step)."""
@@ -68,7 +84,12 @@ def celeba_relative_code(real_code, trans_code):
 
 
 def stn(img, theta23, padding_mode="border"):
-    """transformation_2D.stn (celebA/EAD-GAN_celebA.py:149-153); stock torch op ("next" row f2)."""
+    """transformation_2D.stn (celebA/EAD-GAN_celebA.py:149-153).  When no gradient is requested through it (every
+    consumed gradient of the training steps: the warped images are constants) this is one fused forward kernel;
+    otherwise the stock differentiable torch ops."""
+    needs_grad = torch.is_grad_enabled() and (img.requires_grad or theta23.requires_grad)
+    if _fused(img) and not needs_grad and padding_mode in ("border", "zeros"):
+        return Fn.stn_fwd(img, theta23, border=padding_mode == "border")
     grid = TF.affine_grid(theta23, list(img.shape), align_corners=False)
     return TF.grid_sample(img, grid, padding_mode=padding_mode, align_corners=False)
 
@@ -98,6 +119,13 @@ def dsprites_matrix23(code4):
 
 
 def dsprites_relative_code(real_code, trans_code):
+    """affine_regularzier of dSprites/utils_rp.py:117-147 (fused kernel on CUDA tensors)."""
+    if _fused(real_code, trans_code):
+        return Fn.relative_code(real_code, trans_code, Fn.REL_DSPRITES)
+    return dsprites_relative_code_torch(real_code, trans_code)
+
+
+def dsprites_relative_code_torch(real_code, trans_code):
     """affine_regularzier of dSprites/utils_rp.py:117-147, closed-form inverse (no host round trip)."""
     a1, b1, c1, d1, x1, y1 = _rpt_parts(real_code[:, :4])
     a2, b2, c2, d2, x2, y2 = _rpt_parts(trans_code[:, :4])
@@ -143,6 +171,13 @@ def mnist_matrix23(code7):
 
 
 def mnist_relative_rows(real_code, trans_code):
+    """top two rows of M(trans) @ inverse(M(real)) as [B, 6] (fused kernel on CUDA tensors)."""
+    if _fused(real_code, trans_code):
+        return Fn.relative_code(real_code, trans_code, Fn.REL_MNIST)
+    return mnist_relative_rows_torch(real_code, trans_code)
+
+
+def mnist_relative_rows_torch(real_code, trans_code):
     """top two rows of M(trans) @ inverse(M(real)), flattened to [B, 6] -- the approximator's input
     (MNIST/utils_rpqmnxy.py:123-129); closed-form affine inverse, no host round trip."""
     a1, b1, c1, d1, x1, y1 = _rzst_parts(real_code)

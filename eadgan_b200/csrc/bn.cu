@@ -237,7 +237,8 @@ __device__ __forceinline__ const uint4* row_ptr(const eadgan_tensor4& t, int b, 
   return reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(t.ptr) + (int64_t)b * t.sn + (int64_t)y * t.sh);
 }
 
-struct ChanParams { float mean[8], is[8], ga[8], be[8]; };
+constexpr int NHWC8_U = 4;   // rows processed together by a block (independent loads in flight per thread)
+struct ChanParams { float mean[8], is[8], ga[8], be[8], sc[8], sh[8], nm[8]; };   // sc = is*ga, sh = be - mean*sc, nm = -mean*is
 __device__ __forceinline__ void load_params(ChanParams& p, int ch0, const float* mean, const float* invstd,
                                             const float* gamma, const float* beta) {
 #pragma unroll
@@ -246,6 +247,16 @@ __device__ __forceinline__ void load_params(ChanParams& p, int ch0, const float*
     p.is[j] = invstd[ch0 + j];
     p.ga[j] = gamma ? gamma[ch0 + j] : 1.f;
     p.be[j] = beta ? beta[ch0 + j] : 0.f;
+  }
+}
+// one FMA per element instead of sub/mul/mul/add: y = x*sc + sh, xhat = x*is + nm (bf16 buffers: the fp32
+// re-association is far below the output rounding; apply and the recomputed gate use the SAME expression)
+__device__ __forceinline__ void derive_params(ChanParams& p) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    p.sc[j] = p.is[j] * p.ga[j];
+    p.sh[j] = p.be[j] - p.mean[j] * p.sc[j];
+    p.nm[j] = -p.mean[j] * p.is[j];
   }
 }
 
@@ -257,25 +268,46 @@ __global__ void __launch_bounds__(256) bn_apply_nhwc8_kernel(ApplyArgs a, Nhwc8 
 #pragma unroll
     for (int j = 0; j < 8; ++j) p.is[j] = rsqrtf(p.is[j] + a.eps);
   }
+  derive_params(p);
+  const bool leaky = a.act == EADGAN_ACT_RELU || a.act == EADGAN_ACT_LRELU;
+  const float neg = a.act == EADGAN_ACT_RELU ? 0.f : a.slope;
+  // NHWC8_U rows per block iteration: every thread keeps NHWC8_U independent 16-byte loads in flight (one load
+  // per thread left the kernel latency-bound at ~3 TB/s: 2048 threads x 16 B per SM per memory round trip)
   const int rows = g.n * g.h;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / g.h, y = row - b * g.h;
-    const uint4* xr = row_ptr(a.x, b, y);
-    uint4* yr = const_cast<uint4*>(row_ptr(a.y, b, y));
-    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
-      float f[8];
-      bf8_to_f32(__ldg(xr + v), f);
+  for (int row0 = blockIdx.x * NHWC8_U; row0 < rows; row0 += gridDim.x * NHWC8_U) {
+    const uint4* xr[NHWC8_U];
+    uint4* yr[NHWC8_U];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = eg_act((f[j] - p.mean[j]) * p.is[j] * p.ga[j] + p.be[j], a.act, a.slope);
-      yr[v] = f32_to_bf8(f);
+    for (int u = 0; u < NHWC8_U; ++u) {
+      const int row = min(row0 + u, rows - 1);
+      const int b = row / g.h, y = row - b * g.h;
+      xr[u] = row_ptr(a.x, b, y);
+      yr[u] = const_cast<uint4*>(row_ptr(a.y, b, y));
+    }
+    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
+      uint4 raw[NHWC8_U];
+#pragma unroll
+      for (int u = 0; u < NHWC8_U; ++u) raw[u] = __ldg(xr[u] + v);
+#pragma unroll
+      for (int u = 0; u < NHWC8_U; ++u) {
+        if (row0 + u < rows) {
+          float f[8];
+          bf8_to_f32(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float t = fmaf(f[j], p.sc[j], p.sh[j]);
+            f[j] = leaky ? (t > 0.f ? t : t * neg) : eg_act(t, a.act, a.slope);
+          }
+          yr[u][v] = f32_to_bf8(f);
+        }
+      }
     }
   }
 }
 
 // gate of a ReLU / LeakyReLU that follows the affine transform, recomputed from x exactly as apply did
 __device__ __forceinline__ float bn_gate(float x, const ChanParams& p, int j, float slope_neg) {
-  const float v = (x - p.mean[j]) * p.is[j] * p.ga[j] + p.be[j];
-  return v > 0.f ? 1.f : slope_neg;
+  return fmaf(x, p.sc[j], p.sh[j]) > 0.f ? 1.f : slope_neg;
 }
 
 template <bool GATE_FROM_X>
@@ -286,35 +318,53 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc8_kernel(BwdArgs a, Nhw
   ChanParams p;
   const int ch0 = (threadIdx.x % g.cv) * 8;
   load_params(p, ch0, a.mean, a.invstd, a.gamma, a.beta);
+  derive_params(p);
   const float slope_neg = a.act == EADGAN_ACT_RELU ? 0.f : a.slope;
   float s0[8], s1[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
   const int rows = g.n * g.h;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / g.h, y = row - b * g.h;
-    const uint4* dyr = row_ptr(a.dy, b, y);
-    const uint4* xr = row_ptr(a.x, b, y);
-    const uint4* yr = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
+  for (int row0 = blockIdx.x * NHWC8_U; row0 < rows; row0 += gridDim.x * NHWC8_U) {
+    const uint4 *dyr[NHWC8_U], *xr[NHWC8_U], *yr[NHWC8_U];
+#pragma unroll
+    for (int u = 0; u < NHWC8_U; ++u) {
+      const int row = min(row0 + u, rows - 1);
+      const int b = row / g.h, y = row - b * g.h;
+      dyr[u] = row_ptr(a.dy, b, y);
+      xr[u] = row_ptr(a.x, b, y);
+      yr[u] = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
+    }
     for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
-      float dz[8], xv[8];
-      bf8_to_f32(__ldg(dyr + v), dz);
-      bf8_to_f32(__ldg(xr + v), xv);
-      if (GATE_FROM_X) {
-        if (a.act != EADGAN_ACT_NONE) {
+      uint4 rdz[NHWC8_U], rx[NHWC8_U], ry[NHWC8_U];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
-        }
-      } else {
-        float yv[8];
-        bf8_to_f32(__ldg(yr + v), yv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
+      for (int u = 0; u < NHWC8_U; ++u) {
+        rdz[u] = __ldg(dyr[u] + v);
+        rx[u] = __ldg(xr[u] + v);
+        if (!GATE_FROM_X) ry[u] = __ldg(yr[u] + v);
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        s0[j] += dz[j];
-        s1[j] += dz[j] * (xv[j] - p.mean[j]) * p.is[j];
+      for (int u = 0; u < NHWC8_U; ++u) {
+        if (row0 + u < rows) {
+          float dz[8], xv[8];
+          bf8_to_f32(rdz[u], dz);
+          bf8_to_f32(rx[u], xv);
+          if (GATE_FROM_X) {
+            if (a.act != EADGAN_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
+            }
+          } else {
+            float yv[8];
+            bf8_to_f32(ry[u], yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            s0[j] += dz[j];
+            s1[j] = fmaf(dz[j], fmaf(xv[j], p.is[j], p.nm[j]), s1[j]);
+          }
+        }
       }
     }
   }
@@ -334,40 +384,59 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc8_kernel(BwdArgs a, Nhwc
   load_params(p, ch0, a.mean, a.invstd, a.gamma, a.beta);
   const float slope_neg = a.act == EADGAN_ACT_RELU ? 0.f : a.slope;
   const double inv_count = 1.0 / a.count;
-  float m_dz[8], m_dzx[8];
+  derive_params(p);
+  float c2[8], c3[8];   // dx = sc*dz - sc*mean(dz) - xhat*sc*mean(dz*xhat)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    m_dz[j] = (float)(a.sums[ch0 + j] * inv_count);
-    m_dzx[j] = (float)(a.sums[g.c + ch0 + j] * inv_count);
+    c2[j] = p.sc[j] * (float)(a.sums[ch0 + j] * inv_count);
+    c3[j] = p.sc[j] * (float)(a.sums[g.c + ch0 + j] * inv_count);
   }
   const int rows = g.n * g.h;
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const int b = row / g.h, y = row - b * g.h;
-    const uint4* dyr = row_ptr(a.dy, b, y);
-    const uint4* xr = row_ptr(a.x, b, y);
-    const uint4* yr = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
-    uint4* dxr = const_cast<uint4*>(row_ptr(a.dx, b, y));
+  for (int row0 = blockIdx.x * NHWC8_U; row0 < rows; row0 += gridDim.x * NHWC8_U) {
+    const uint4 *dyr[NHWC8_U], *xr[NHWC8_U], *yr[NHWC8_U];
+    uint4* dxr[NHWC8_U];
+#pragma unroll
+    for (int u = 0; u < NHWC8_U; ++u) {
+      const int row = min(row0 + u, rows - 1);
+      const int b = row / g.h, y = row - b * g.h;
+      dyr[u] = row_ptr(a.dy, b, y);
+      xr[u] = row_ptr(a.x, b, y);
+      yr[u] = GATE_FROM_X ? nullptr : row_ptr(a.y, b, y);
+      dxr[u] = const_cast<uint4*>(row_ptr(a.dx, b, y));
+    }
     for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
-      float dz[8], xv[8];
-      bf8_to_f32(__ldg(dyr + v), dz);
-      bf8_to_f32(__ldg(xr + v), xv);
-      if (GATE_FROM_X) {
-        if (a.act != EADGAN_ACT_NONE) {
+      uint4 rdz[NHWC8_U], rx[NHWC8_U], ry[NHWC8_U];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
+      for (int u = 0; u < NHWC8_U; ++u) {
+        rdz[u] = __ldg(dyr[u] + v);
+        rx[u] = __ldg(xr[u] + v);
+        if (!GATE_FROM_X) ry[u] = __ldg(yr[u] + v);
+      }
+#pragma unroll
+      for (int u = 0; u < NHWC8_U; ++u) {
+        if (row0 + u < rows) {
+          float dz[8], xv[8];
+          bf8_to_f32(rdz[u], dz);
+          bf8_to_f32(rx[u], xv);
+          if (GATE_FROM_X) {
+            if (a.act != EADGAN_ACT_NONE) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) dz[j] *= bn_gate(xv[j], p, j, slope_neg);
+            }
+          } else {
+            float yv[8];
+            bf8_to_f32(ry[u], yv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xhat = fmaf(xv[j], p.is[j], p.nm[j]);
+            dz[j] = fmaf(-xhat, c3[j], fmaf(dz[j], p.sc[j], -c2[j]));
+          }
+          dxr[u][v] = f32_to_bf8(dz);
         }
-      } else {
-        float yv[8];
-        bf8_to_f32(__ldg(yr + v), yv);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dz[j] *= eg_act_grad(yv[j], a.act, a.slope);
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float xhat = (xv[j] - p.mean[j]) * p.is[j];
-        dz[j] = p.ga[j] * p.is[j] * (dz[j] - m_dz[j] - xhat * m_dzx[j]);
-      }
-      dxr[v] = f32_to_bf8(dz);
     }
   }
 }
@@ -384,8 +453,8 @@ bool nhwc8_ok(const Geo& g, const eadgan_tensor4* const* ts, int nt) {
 }
 Nhwc8 make_nhwc8(const Geo& g) { return Nhwc8{g.n, g.c, g.h, g.w, g.c / 8, g.w * g.c / 8}; }
 int nhwc8_grid(const Geo& g) {
-  const int rows = g.n * g.h, cap = 8 * eg_sm_count();
-  return rows < cap ? rows : cap;
+  const int groups = (g.n * g.h + NHWC8_U - 1) / NHWC8_U, cap = 8 * eg_sm_count();
+  return groups < cap ? groups : cap;
 }
 
 __global__ void bn_finalize_kernel(const double* sums, double count, int c, float eps, float momentum,

@@ -1292,33 +1292,46 @@ namespace {
 __global__ void __launch_bounds__(256) thin_expand_kernel(eadgan_tensor4 src, eadgan_tensor4 mask, int act, float slope,
                                                           int n, int c_real, int h, int w,
                                                           __nv_bfloat16* __restrict__ R) {
+  // one thread per (n, oy, X): up to 12 independent loads in flight, one 32-byte store
   const int p = h / 2, wp = w + 2;
-  const int64_t total = (int64_t)n * p * wp * 4;
+  const int64_t total = (int64_t)n * p * wp;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ky = (int)(i & 3);
-    int64_t r = i >> 2;
+    int64_t r = i;
     const int X = (int)(r % wp); r /= wp;
     const int oy = (int)(r % p);
     const int b = (int)(r / p);
-    const int y = 2 * oy + ky - 1, x = X - 1;
-    float v[4] = {0.f, 0.f, 0.f, 0.f};
-    if (y >= 0 && y < h && x >= 0 && x < w) {
+    const int x = X - 1;
+    float v[4][4], m[4][4];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      const int y = 2 * oy + ky - 1;
+      const bool in = y >= 0 && y < h && x >= 0 && x < w;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        if (c < c_real) {
-          v[c] = eg_ld(src.ptr, (int64_t)b * src.sn + (int64_t)c * src.sc + (int64_t)y * src.sh + (int64_t)x * src.sw,
-                       src.dtype);
+        v[ky][c] = 0.f; m[ky][c] = 0.f;
+        if (in && c < c_real) {
+          v[ky][c] = eg_ld(src.ptr, (int64_t)b * src.sn + (int64_t)c * src.sc + (int64_t)y * src.sh + (int64_t)x * src.sw,
+                           src.dtype);
           if (act != EADGAN_ACT_NONE)
-            v[c] *= eg_act_grad(eg_ld(mask.ptr, (int64_t)b * mask.sn + (int64_t)c * mask.sc + (int64_t)y * mask.sh +
-                                                    (int64_t)x * mask.sw, mask.dtype), act, slope);
+            m[ky][c] = eg_ld(mask.ptr, (int64_t)b * mask.sn + (int64_t)c * mask.sc + (int64_t)y * mask.sh +
+                                           (int64_t)x * mask.sw, mask.dtype);
         }
       }
     }
-    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&lo);
-    pk.y = *reinterpret_cast<uint32_t*>(&hi);
-    *reinterpret_cast<uint2*>(R + i * 4) = pk;
+    uint32_t pk[8];
+#pragma unroll
+    for (int ky = 0; ky < 4; ++ky) {
+      if (act != EADGAN_ACT_NONE) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[ky][c] *= eg_act_grad(m[ky][c], act, slope);
+      }
+      __nv_bfloat162 lo = __floats2bfloat162_rn(v[ky][0], v[ky][1]), hi = __floats2bfloat162_rn(v[ky][2], v[ky][3]);
+      pk[2 * ky] = *reinterpret_cast<uint32_t*>(&lo);
+      pk[2 * ky + 1] = *reinterpret_cast<uint32_t*>(&hi);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(R + i * 16);
+    dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
 }
 
@@ -1542,7 +1555,7 @@ extern "C" int eadgan_tc_thin_expand(const eadgan_tensor4* src, const eadgan_ten
   EG_REQUIRE(src && src->ptr && r_out && n > 0 && c_real >= 1 && c_real <= 4 && h >= 2 && w >= 2 && h % 2 == 0 &&
                  w % 2 == 0, EADGAN_ERR_INVALID, "tc_thin_expand: bad arguments");
   EG_REQUIRE(act == EADGAN_ACT_NONE || (mask && mask->ptr), EADGAN_ERR_INVALID, "tc_thin_expand: act without mask");
-  const int64_t total = (int64_t)n * (h / 2) * (w + 2) * 4;
+  const int64_t total = (int64_t)n * (h / 2) * (w + 2);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 32 * eg_sm_count()) blocks = 32 * eg_sm_count();
   eadgan_tensor4 mk = mask ? *mask : *src;

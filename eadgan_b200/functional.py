@@ -495,3 +495,72 @@ def cross_entropy(x, labels):
 def mutual_info_loss(q, c):
     """dSprites/rp.py:225-232; the target c carries no gradient (one-hot or detached)."""
     return _MIFn.apply(q, c.detach())
+
+
+# ---- fused affine glue (csrc/glue.cu) ----------------------------------------------------------------------
+REL_CELEBA, REL_DSPRITES, REL_MNIST = 0, 1, 2
+_REL_DIMS = {REL_CELEBA: (5, 5), REL_DSPRITES: (4, 4), REL_MNIST: (7, 6)}
+
+
+def _rows(t, k, who):
+    """[B, >=k] fp32 CUDA tensor with unit column stride -> (tensor kept alive, row stride)"""
+    if not (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.shape[1] >= k):
+        raise RuntimeError(f"{who}: expected a CUDA fp32 [B, >= {k}] tensor")
+    if t.stride(1) != 1:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+class _RelCodeFn(torch.autograd.Function):
+    """relative affine code of two code vectors (mode-specific closed form) with a stored Jacobian"""
+
+    @staticmethod
+    def forward(ctx, real, trans, mode):
+        k, ko = _REL_DIMS[mode]
+        real_k, rs = _rows(real.detach(), k, "relative_code")
+        trans_k, ts = _rows(trans.detach(), k, "relative_code")
+        n = real.shape[0]
+        out = torch.empty((n, ko), device=real.device, dtype=torch.float32)
+        jac = torch.empty((n, ko, 2 * k), device=real.device, dtype=torch.float32)
+        call("eadgan_relcode_fwd", mode, ptr(real_k), rs, ptr(trans_k), ts, n, ptr(out), ptr(jac), stream())
+        ctx.save_for_backward(jac)
+        ctx.cfg = (mode, k, real.shape[1], trans.shape[1])
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (jac,) = ctx.saved_tensors
+        mode, k, real_w, trans_w = ctx.cfg
+        n = jac.shape[0]
+        g = g.contiguous()
+        # gradients w.r.t. the first k columns; any further columns of the inputs get zero
+        d_real = torch.zeros((n, real_w), device=g.device, dtype=torch.float32) if real_w != k else None
+        d_trans = torch.zeros((n, trans_w), device=g.device, dtype=torch.float32) if trans_w != k else None
+        dr = torch.empty((n, k), device=g.device, dtype=torch.float32)
+        dt = torch.empty((n, k), device=g.device, dtype=torch.float32)
+        call("eadgan_relcode_bwd", mode, ptr(g), ptr(jac), n, ptr(dr), ptr(dt), stream())
+        if d_real is not None:
+            d_real[:, :k] = dr
+            dr = d_real
+        if d_trans is not None:
+            d_trans[:, :k] = dt
+            dt = d_trans
+        return dr, dt, None
+
+
+def relative_code(real, trans, mode):
+    return _RelCodeFn.apply(real, trans, mode)
+
+
+def stn_fwd(img, theta23, border=True):
+    """F.grid_sample(img, F.affine_grid(theta, img.size()), padding_mode) with align_corners=False; forward only."""
+    if not (img.is_cuda and img.dtype == torch.float32 and img.dim() == 4):
+        raise RuntimeError("stn_fwd: expected a CUDA fp32 [N, C, H, W] image")
+    img = img.contiguous()
+    theta = theta23.detach().to(torch.float32).contiguous()
+    n, c, h, w = img.shape
+    if tuple(theta.shape) != (n, 2, 3):
+        raise RuntimeError("stn_fwd: theta must be [N, 2, 3]")
+    out = torch.empty_like(img)
+    call("eadgan_stn_fwd", ptr(img), ptr(theta), n, c, h, w, 1 if border else 0, ptr(out), stream())
+    return out

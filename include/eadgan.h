@@ -344,6 +344,24 @@ int eadgan_f64_to_f32(const double* src, float* dst, int64_t numel, void* stream
  * left untouched (it is fully overwritten by the producing kernel's epilogue) */
 int eadgan_zero_halo(void* xp, int n, int h, int w, int c, void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Affine glue.                               */
+/* stn_fwd: transformation_2D.stn = F.grid_sample(x, F.affine_grid(theta, x.size()),
+ * padding_mode) with align_corners = False (celebA/EAD-GAN_celebA.py:149-153; 'border' everywhere
+ * but colored_dSprites/pxy_color.py:90).  img/out fp32 NCHW contiguous, theta fp32 [n,2,3].
+ * relcode: "affine_regularzier" in closed form with its Jacobian (forward-mode), mode 0 =
+ * celebA/utils_rpqxy.py:82-116 (5 codes -> 5), 1 = dSprites/utils_rp.py:117-147 (4 -> 4), 2 = the 2x3
+ * rows of trans @ inverse(real) fed to MNIST's approximator (MNIST/utils_rpqmnxy.py:117-129; 7 -> 6).
+ * real/trans: rows of >= k_in floats at the given row strides; out [n,k_out]; jac [n,k_out,2*k_in].  */
+/* ------------------------------------------------------------------------- */
+int eadgan_stn_fwd(const float* img, const float* theta, int n, int c, int h, int w, int padding_border,
+                   float* out, void* stream);
+int eadgan_relcode_dims(int mode, int* k_in, int* k_out);
+int eadgan_relcode_fwd(int mode, const float* real, long long real_stride, const float* trans,
+                       long long trans_stride, int n, float* out, float* jac, void* stream);
+int eadgan_relcode_bwd(int mode, const float* g, const float* jac, int n, float* d_real, float* d_trans,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif
