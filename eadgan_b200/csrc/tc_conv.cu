@@ -633,6 +633,7 @@ struct WgParams {
   float* partial;       // [splits][k][16c]
   int dense;            // 1: "pixels" are batch rows; A boxes from a [n][Mp] matrix, B boxes from [n,6,6,C]
   int thin;             // 1: big map is a <= 4-channel image; B = one 64-wide patch box of the row-expanded buffer
+  int kk_tiles, ko_tiles, splits;   // persistent item space (filled by launch_wgrad from the logical grid)
 };
 
 template <int BLOCK_N>  // BLOCK_N columns of kk per tile (multiple of 64)
@@ -648,6 +649,9 @@ template <int BLOCK_N>
 __global__ void __launch_bounds__(192, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgParams P) {
+  // PERSISTENT: work items are (split, ko tile, kk tile) triples, kk fastest; CTA c runs items c, c + grid, ...
+  // Two TMEM accumulators: the epilogue of item i (128 x BLOCK_N fp32 partial -> global) overlaps the
+  // mainloop of item i + 1, and barrier / TMEM / tensor-map set-up is paid once per CTA instead of per item.
   using C = WgCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSETTING the shared array (not by integer round trip): the compiler keeps the shared address
@@ -655,24 +659,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + C::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + C::STAGES;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kk_tile = blockIdx.x, ko_tile = blockIdx.y, split = blockIdx.z;
-  const int step0 = split * P.steps_per_split;
-  const int step1 = min(P.steps_total, step0 + P.steps_per_split);
-  const int nsteps = step1 - step0;
+  const int tiles = P.kk_tiles * P.ko_tiles;
+  const int total_items = tiles * P.splits;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, BLOCK_N);
+    tmem_alloc(tmem_ptr, 2 * BLOCK_N);
   }
   tc_fence_before();
   __syncthreads();
@@ -682,89 +685,120 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int st = step0; st < step1; ++st) {
-        mbar_wait(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * C::STAGE_BYTES;
-        uint8_t* sb = sa + C::A_B;
-        mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-        if (P.dense) {
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int kk_tile = item % P.kk_tiles, ko_tile = (item / P.kk_tiles) % P.ko_tiles, split = item / tiles;
+        const int step0 = split * P.steps_per_split;
+        const int step1 = min(P.steps_total, step0 + P.steps_per_split);
+        for (int st = step0; st < step1; ++st) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_B;
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (P.dense) {
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_2d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, st * 64);
+            for (int h = 0; h < 2; ++h)
+              tma_load_2d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, st * 64);
 #pragma unroll
-          for (int i = 0; i < BLOCK_N / 64; ++i) {
-            const int nb = kk_tile * (BLOCK_N / 64) + i;
-            const int qi = nb % P.qblocks, tap = nb / P.qblocks;  // tap = ky*4+kx
-            tma_load_4d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
+            for (int i = 0; i < BLOCK_N / 64; ++i) {
+              const int nb = kk_tile * (BLOCK_N / 64) + i;
+              const int qi = nb % P.qblocks, tap = nb / P.qblocks;  // tap = ky*4+kx
+              tma_load_4d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
+            }
+          } else {
+            const int b0 = (st / P.tiles_y) * P.Tb;
+            const int y0 = (st % P.tiles_y) * P.Th;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+            if (P.thin) {
+              tma_load_4d(sb, &map_x, &full_bar[stage], 0, 0, y0, b0);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BLOCK_N / 64; ++i) {
+                const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
+                const int qi = nb % P.qblocks, t = nb / P.qblocks;
+                const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+                tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
+              }
+            }
           }
-        } else {
-          const int b0 = (st / P.tiles_y) * P.Tb;
-          const int y0 = (st % P.tiles_y) * P.Th;
-#pragma unroll
-          for (int h = 0; h < 2; ++h)
-            tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
-          if (P.thin) {
-            tma_load_4d(sb, &map_x, &full_bar[stage], 0, 0, y0, b0);
-          } else
-#pragma unroll
-          for (int i = 0; i < BLOCK_N / 64; ++i) {
-            const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
-            const int qi = nb % P.qblocks, t = nb / P.qblocks;
-            const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-            tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
-          }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);  // both operands MN-major
     int stage = 0; uint32_t phase = 0;
-    for (int it = 0; it < nsteps; ++it) {
-      mbar_wait(&full_bar[stage], phase);
+    int use = 0;   // accumulator uses so far (items with at least one step)
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int split = item / tiles;
+      const int step0 = split * P.steps_per_split;
+      const int nsteps = min(P.steps_total, step0 + P.steps_per_split) - step0;
+      if (nsteps <= 0) continue;
+      const int buf = use & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((use >> 1) & 1) ^ 1);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-        const uint32_t sb = sa + C::A_B;
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * BLOCK_N);
+      for (int it = 0; it < nsteps; ++it) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_B;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixel rows per MMA
-          const uint64_t da = make_desc(sa + k * 2048, 8192, 1024);
-          const uint64_t db = make_desc(sb + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < 4; ++k) {  // 16 pixel rows per MMA
+            const uint64_t da = make_desc(sa + k * 2048, 8192, 1024);
+            const uint64_t db = make_desc(sb + k * 2048, 8192, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (it == nsteps - 1) umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (it == nsteps - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      ++use;
     }
   } else {
     const int quad = warp & 3;
-    const int ko = ko_tile * 128 + quad * 32 + lane;
-    if (nsteps > 0) {
-      mbar_wait(tmem_full_bar, 0);
-      tc_fence_after();
-    }
-    float* dst = P.partial + ((int64_t)split * P.k + ko) * P.Ktot + (int64_t)kk_tile * BLOCK_N;
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-      float v[32];
+    int use = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int kk_tile = item % P.kk_tiles, ko_tile = (item / P.kk_tiles) % P.ko_tiles, split = item / tiles;
+      const int step0 = split * P.steps_per_split;
+      const int nsteps = min(P.steps_total, step0 + P.steps_per_split) - step0;
+      const int ko = ko_tile * 128 + quad * 32 + lane;
+      const int buf = use & 1;
       if (nsteps > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        mbar_wait(&tmem_full_bar[buf], (use >> 1) & 1);
+        tc_fence_after();
       }
-      if (ko < P.k) {
+      float* dst = P.partial + ((int64_t)split * P.k + ko) * P.Ktot + (int64_t)kk_tile * BLOCK_N;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        if (nsteps > 0) {
+          tmem_ld32(tmem_base + (uint32_t)(buf * BLOCK_N) + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+          if (c0 + 32 >= BLOCK_N) {   // every column of this warp's rows is in registers: release the accumulator
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
+        } else {
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
-          *reinterpret_cast<float4*>(dst + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (ko < P.k) {
+#pragma unroll
+          for (int g = 0; g < 8; ++g)
+            *reinterpret_cast<float4*>(dst + c0 + g * 4) = make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
+        }
       }
+      if (nsteps > 0) ++use;
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, BLOCK_N);
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
 }
 
 // sum split partials and permute GEMM column order (a,b,dy,dx,c) -> dw[ko][c][ky][kx]
@@ -1111,7 +1145,7 @@ int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
     const int s_eff = (P->steps_total + sps - 1) / sps;
     const int64_t ctas = (int64_t)tiles * s_eff;
     const int64_t waves = (ctas + sms - 1) / sms;
-    const double t_mma = (double)waves * (sps * (*bn) * 2.0 + 6000.0) / 1.9e9 / 0.9;  // + per-CTA prologue/epilogue
+    const double t_mma = (double)waves * (sps * (*bn) * 2.0 + 1500.0) / 1.9e9 / 0.9;  // + pipeline refill per item
     const double t_part = (double)s_eff * k_pad * (double)P->Ktot * 8.0 / 6.0e12;
     if (t_mma + t_part < best) { best = t_mma + t_part; best_s = s_eff; }
   }
@@ -1127,7 +1161,15 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& 
     EG_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM));
     attr_set = true;
   }
-  tc_wgrad_kernel<BN><<<grid, 192, WgCfg<BN>::SMEM, st>>>(mdy, mx, P);
+  // `grid` is the logical item space (kk tiles, ko tiles, splits); the launch is one CTA per SM at most, every
+  // CTA running the same number of items (+-1)
+  WgParams Q = P;
+  Q.kk_tiles = (int)grid.x; Q.ko_tiles = (int)grid.y; Q.splits = (int)grid.z;
+  const int total = Q.kk_tiles * Q.ko_tiles * Q.splits;
+  const int sms = eg_sm_count();
+  const int waves = (total + sms - 1) / sms;
+  const int ctas = (total + waves - 1) / waves;
+  tc_wgrad_kernel<BN><<<ctas, 192, WgCfg<BN>::SMEM, st>>>(mdy, mx, Q);
   EG_LAUNCH_CHECK("tc_wgrad_kernel");
   return 0;
 }
