@@ -57,7 +57,7 @@ _PROTOS = {
     "eadgan_tc_pack_w_fprop": [_P, _P, _I, _I, _I, _P, _P],
     "eadgan_tc_pack_w_dgrad": [_P, _P, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_pack": [_P, _I, _I, _I, _I, _P, _P],
-    "eadgan_tc_dense_gather": [_P, _P, _P, _P, _I, _I, _I, _P],
+    "eadgan_tc_dense_gather": [_P, _P, _P, _P, _I, _I, _I, _P, C.c_size_t, _P],
     "eadgan_tc_dense_scatter": [_P, _P, _P, _P, _P, _I, _F, _I, _I, _I, _P, _P],
     "eadgan_tc_dense_wgrad": [_P, _P, _P, _P, C.c_size_t, _I, _I, _I, _I, _P],
     "eadgan_tc_fprop": [C.POINTER(TcDesc), _P, _P, _P, _P, _P, _P, _P, _P],
@@ -112,6 +112,7 @@ _SPECIAL = {
     "eadgan_tc_workspace_bytes": ([C.POINTER(TcDesc), _I], C.c_size_t),
     "eadgan_conv_wgrad_workspace": ([C.POINTER(ConvDesc)], C.c_size_t),
     "eadgan_tc_thin_buffer_elems": ([_I, _I, _I], C.c_size_t),
+    "eadgan_tc_dense_gather_workspace": ([_I], C.c_size_t),
     "eadgan_tc_thin_wgrad_workspace": ([C.POINTER(TcDesc)], C.c_size_t),
     "eadgan_tc_dense_wgrad_workspace": ([_I, _I], C.c_size_t),
     "eadgan_spectral_norm_scratch_floats": ([_I, _I, _I], C.c_size_t),

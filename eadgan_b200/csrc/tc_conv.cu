@@ -262,6 +262,7 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& P, int tile, int h, 
       ri.f32_out = false;
     } else {
       ri.out_off = (int64_t)m * P.n_store + n0;
+      if (P.mode == MODE_DENSE_GATHER) ri.out_off += (int64_t)parity * P.gemm_m * P.n_store;   // split-K slab
       ri.f32_out = true;
     }
   } else {
@@ -355,7 +356,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + MT * A_BYTES;
           mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
-          const int qi = kb % P.qblocks, t = kb / P.qblocks;
+          // dense gather: the K range (16 taps x channels) is split over the "parity" index (split-K)
+          const int kbg = P.mode == MODE_DENSE_GATHER ? parity * P.nkb + kb : kb;
+          const int qi = kbg % P.qblocks, t = kbg / P.qblocks;
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
             const int m_tile = m_grp * MT + h;
@@ -381,7 +384,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-          tma_load_2d(sb, &map_b, &full_bar[stage], kb * BLOCK_K,
+          tma_load_2d(sb, &map_b, &full_bar[stage], kbg * BLOCK_K,
                       (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -867,35 +870,49 @@ __global__ void dense_pack_kernel(const float* __restrict__ w, int m_real, int m
 // ------------------------------------------------------------------------------------
 // weight packing
 // ------------------------------------------------------------------------------------
-// Wf[ko][((a*2+b)*2+dy)*2c + dx*c + ci] = w[ko][ci][2a+dy][2b+dx] / sigma
-__global__ void pack_w_fprop_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c_real,
-                                    int c, __nv_bfloat16* __restrict__ out) {
+// Wf[ko][((a*2+b)*2+dy)*2c + dx*c + ci] = w[ko][ci][2a+dy][2b+dx] / sigma, i.e. per ko a [c][16] -> [16][c]
+// transpose with a tap permutation.  Block = (64-channel chunk, ko): coalesced 4 KB read, sixteen 128-byte writes.
+__global__ void __launch_bounds__(256) pack_w_fprop_kernel(const float* __restrict__ w, const float* __restrict__ sigma,
+                                                           int k, int c_real, int c, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][17];
   const float inv = sigma ? 1.f / *sigma : 1.f;
-  const int64_t total = (int64_t)k * 16 * c;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int ko = (int)(i / (16 * c));
-    const int col = (int)(i - (int64_t)ko * 16 * c);
-    const int t3 = col / (2 * c), rem = col - t3 * 2 * c;
-    const int dx = rem / c, ci = rem - dx * c;
-    const int dy = t3 & 1, bt = (t3 >> 1) & 1, at = t3 >> 2;
-    const int ky = 2 * at + dy, kx = 2 * bt + dx;
-    out[i] = __float2bfloat16_rn(ci < c_real ? w[(((int64_t)ko * c_real + ci) * 4 + ky) * 4 + kx] * inv : 0.f);
+  const int ko = blockIdx.y, c0 = blockIdx.x * 64;
+  for (int e = threadIdx.x; e < 64 * 16; e += 256) {
+    const int cl = e >> 4, tp = e & 15;   // tp = ky*4 + kx
+    tile[cl][tp] = (c0 + cl < c_real) ? w[((int64_t)ko * c_real + c0 + cl) * 16 + tp] * inv : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 16 * 64; e += 256) {
+    const int tap = e >> 6, cl = e & 63;  // tap = ((a*2+b)*2+dy)*2+dx
+    if (c0 + cl < c) {
+      const int dx = tap & 1, dy = (tap >> 1) & 1, bt = (tap >> 2) & 1, at = tap >> 3;
+      out[(int64_t)ko * 16 * c + (int64_t)tap * c + c0 + cl] = __float2bfloat16_rn(tile[cl][(2 * at + dy) * 4 + 2 * bt + dx]);
+    }
   }
 }
-// Wd[(py*2+px)*c + co][(ty*2+tx)*k + ki] = w[ki][co][ky(py,ty)][kx(px,tx)] / sigma
-__global__ void pack_w_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ sigma, int k, int c_real,
-                                    int c, __nv_bfloat16* __restrict__ out) {
+// Wd[(py*2+px)*c + co][(ty*2+tx)*k + ki] = w[ki][co][ky(py,ty)][kx(px,tx)] / sigma.  Block = (64 ki, 8 co): reads
+// 512-byte runs (8 co x 16 taps of one ki), writes 128-byte runs (64 ki of one (parity, co, tap)).
+__global__ void __launch_bounds__(256) pack_w_dgrad_kernel(const float* __restrict__ w, const float* __restrict__ sigma,
+                                                           int k, int c_real, int c, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][129];
   const float inv = sigma ? 1.f / *sigma : 1.f;
-  const int64_t total = (int64_t)4 * c * 4 * k;
-  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int rowi = (int)(i / (4 * k));
-    const int col = (int)(i - (int64_t)rowi * 4 * k);
-    const int par = rowi / c, co = rowi - par * c;
-    const int t = col / k, ki = col - t * k;
-    const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
-    const int ky = py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2);
-    const int kx = px == 0 ? (tx == 0 ? 1 : 3) : (tx == 0 ? 0 : 2);
-    out[i] = __float2bfloat16_rn(co < c_real ? w[(((int64_t)ki * c_real + co) * 4 + ky) * 4 + kx] * inv : 0.f);
+  const int ki0 = blockIdx.x * 64, co0 = blockIdx.y * 8;
+  for (int e = threadIdx.x; e < 64 * 128; e += 256) {
+    const int kl = e >> 7, r = e & 127;   // r = co_local*16 + ky*4 + kx
+    const int co = co0 + (r >> 4);
+    tile[kl][r] = (ki0 + kl < k && co < c_real) ? w[((int64_t)(ki0 + kl) * c_real + co) * 16 + (r & 15)] * inv : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 128 * 64; e += 256) {
+    const int combo = e >> 6, kl = e & 63;     // combo = (co_local*4 + par)*4 + t
+    const int t = combo & 3, par = (combo >> 2) & 3, col = combo >> 4;
+    const int co = co0 + col;
+    if (co < c && ki0 + kl < k) {
+      const int py = par >> 1, px = par & 1, ty = t >> 1, tx = t & 1;
+      const int ky = py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2);
+      const int kx = px == 0 ? (tx == 0 ? 1 : 3) : (tx == 0 ? 0 : 2);
+      out[((int64_t)par * c + co) * 4 * k + (int64_t)t * k + ki0 + kl] = __float2bfloat16_rn(tile[kl][col * 16 + ky * 4 + kx]);
+    }
   }
 }
 
@@ -1044,10 +1061,8 @@ extern "C" int eadgan_tc_pack_w_fprop(const float* w, const float* sigma, int k,
                                       void* stream) {
   EG_REQUIRE(w && w_packed && k > 0 && c > 0 && c_real > 0 && c_real <= c, EADGAN_ERR_INVALID,
              "tc_pack_w_fprop: bad arguments");
-  const int64_t total = (int64_t)k * 16 * c;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
-  pack_w_fprop_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c, (__nv_bfloat16*)w_packed);
+  pack_w_fprop_kernel<<<dim3((c + 63) / 64, k), 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c,
+                                                                                (__nv_bfloat16*)w_packed);
   EG_LAUNCH_CHECK("pack_w_fprop_kernel");
   return 0;
 }
@@ -1056,10 +1071,8 @@ extern "C" int eadgan_tc_pack_w_dgrad(const float* w, const float* sigma, int k,
                                       void* stream) {
   EG_REQUIRE(w && w_packed && k > 0 && c > 0 && c_real > 0 && c_real <= c, EADGAN_ERR_INVALID,
              "tc_pack_w_dgrad: bad arguments");
-  const int64_t total = (int64_t)k * 16 * c;
-  int blocks = (int)((total + 255) / 256);
-  if (blocks > 16 * eg_sm_count()) blocks = 16 * eg_sm_count();
-  pack_w_dgrad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c, (__nv_bfloat16*)w_packed);
+  pack_w_dgrad_kernel<<<dim3((k + 63) / 64, (c + 7) / 8), 256, 0, (cudaStream_t)stream>>>(w, sigma, k, c_real, c,
+                                                                                          (__nv_bfloat16*)w_packed);
   EG_LAUNCH_CHECK("pack_w_dgrad_kernel");
   return 0;
 }
@@ -1255,18 +1268,41 @@ extern "C" int eadgan_tc_dense_pack(const float* w, int m_real, int m_pad, int C
   return 0;
 }
 
-// out[b][j] (fp32, j < m_real) = bias[j] + sum_{tap,c} Y[b][tap][c] * Wp[j][tap*C + c]
+namespace {
+constexpr int GATHER_SPLITS = 16;   // one split per tap: 8 M tiles x 16 splits fill the machine at batch 1024
+__global__ void dense_gather_sum_kernel(const float* __restrict__ partial, const float* __restrict__ bias, int n,
+                                        int m_real, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * m_real) return;
+  const int b = i / m_real, j = i - b * m_real;
+  float s = bias ? bias[j] : 0.f;
+  for (int sp = 0; sp < GATHER_SPLITS; ++sp) s += partial[((int64_t)sp * n + b) * 32 + j];
+  out[i] = s;
+}
+}  // namespace
+
+extern "C" size_t eadgan_tc_dense_gather_workspace(int n) { return (size_t)GATHER_SPLITS * n * 32 * sizeof(float); }
+
+// out[b][j] (fp32, j < m_real) = bias[j] + sum_{tap,c} Y[b][tap][c] * Wp[j][tap*C + c].  K = 16 C is long and
+// M = n, N = 32 give only n/128 tiles, so the K range is split per tap over CTAs (fp32 slabs in the caller's
+// workspace, summed in a fixed order: deterministic).
 extern "C" int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, const float* bias, float* out, int n,
-                                      int C, int m_real, void* stream) {
+                                      int C, int m_real, void* workspace, size_t ws_bytes, void* stream) {
   EG_REQUIRE(y_pad && w_rows && out && n > 0 && m_real > 0, EADGAN_ERR_INVALID, "tc_dense_gather: bad arguments");
   EG_REQUIRE(C % 64 == 0 && m_real <= 32, EADGAN_ERR_UNSUPPORTED, "tc_dense_gather: needs C%%64==0 and m<=32");
+  EG_REQUIRE(workspace && ws_bytes >= eadgan_tc_dense_gather_workspace(n), EADGAN_ERR_WORKSPACE,
+             "tc_dense_gather: workspace %zu < %zu bytes", ws_bytes, eadgan_tc_dense_gather_workspace(n));
   TcParams P{};
-  P.mode = MODE_DENSE_GATHER; P.qblocks = C / 64; P.nkb = 16 * P.qblocks; P.gemm_m = n; P.gemm_n = 32;
-  P.N_total = 32; P.n_store = m_real; P.bias = bias; P.out = out;
+  P.mode = MODE_DENSE_GATHER; P.qblocks = C / 64; P.nkb = P.qblocks /* per split: one tap */; P.gemm_m = n; P.gemm_n = 32;
+  P.N_total = 32; P.n_store = 32; P.bias = nullptr; P.out = workspace;
   CUtensorMap ma, mb;
   if (int e = map_pad6(&ma, y_pad, n, C, 128)) return e;
   if (int e = map_matrix(&mb, w_rows, 32, (uint64_t)16 * C, 32)) return e;
-  return dispatch_conv(32, ma, mb, P, (n + 127) / 128, 32, 1, (cudaStream_t)stream);
+  if (int e = dispatch_conv(32, ma, mb, P, (n + 127) / 128, 32, GATHER_SPLITS, (cudaStream_t)stream)) return e;
+  dense_gather_sum_kernel<<<(n * m_real + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, bias, n,
+                                                                                      m_real, out);
+  EG_LAUNCH_CHECK("dense_gather_sum_kernel");
+  return 0;
 }
 
 // Out[b][1+ky][1+kx][ch] (padded NHWC bf16) = (bias[ch] + sum_j A[b][j] * Wp[tap*C + ch][j]) * mask'(.)

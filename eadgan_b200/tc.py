@@ -169,7 +169,9 @@ def dense_pack(w, m_pad, rows_major):
 def dense_gather(yp, w_rows, bias, m_real):
     n, _, _, Cc = yp.shape
     out = torch.empty((n, m_real), device=yp.device, dtype=torch.float32)
-    call("eadgan_tc_dense_gather", ptr(yp), ptr(w_rows), ptr(bias), ptr(out), n, Cc, m_real, stream())
+    ws = _workspace(L.lib().eadgan_tc_dense_gather_workspace(n), yp.device)
+    call("eadgan_tc_dense_gather", ptr(yp), ptr(w_rows), ptr(bias), ptr(out), n, Cc, m_real, ptr(ws),
+         C.c_size_t(ws.numel()), stream())
     return out
 
 

@@ -199,8 +199,9 @@ int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void
  *   wgrad  : dw[m_real][C][4][4] fp32 = A^T . Y            (both weight gradients) */
 int eadgan_tc_dense_pack(const float* w, int m_real, int m_pad, int C, int rows_major, void* out,
                          void* stream);
+size_t eadgan_tc_dense_gather_workspace(int n);
 int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, const float* bias, float* out, int n,
-                           int C, int m_real, void* stream);
+                           int C, int m_real, void* workspace, size_t ws_bytes, void* stream);
 int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, const float* bias, void* out_pad,
                             const void* mask, int mask_act, float slope, int n, int C, int m_pad,
                             double* chan_sums /* NULL, or fp64 [C]: per-channel sums of the result */,
