@@ -30,6 +30,18 @@ METRIC = "train images/sec (G+D+E step, 64x64 CelebA)"
 GFLOP_PER_IMG = 18.865  # useful algorithmic GFLOP / image / step
 
 
+def ncu_traffic(entry_name):
+    """DRAM bytes per launch of this entry point's kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/ncu_summarize.py), or None when it was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            t = json.load(f).get(entry_name)
+        return None if t is None else {"bytes": t["dram_bytes_per_launch"], "capture": t["capture"],
+                                       "tensor_pipe_pct": t.get("tensor_pipe_pct")}
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -240,8 +252,13 @@ def main():
     if conv:
         name, r = max(conv.items(), key=lambda kv: kv[1]["ms"])
         ach = r["flops"] / (r["ms"] * 1e-3) / 1e12
+        tr = ncu_traffic(name)
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sust"], "traffic": None, "kernel": name, "launches": r["calls"],
+                "frac": ach / pk["tf_sust"], "traffic": None if tr is None else tr["bytes"],
+                "traffic_source": None if tr is None else f"profiles/{tr['capture']} (ncu --set full, dram read + write per launch)",
+                "ncu_tensor_pipe_pct": None if tr is None else tr["tensor_pipe_pct"],
+                "algorithmic_flops_per_launch": r["flops"] / r["calls"],
+                "kernel": name, "launches": r["calls"],
                 "avg_launch_ms": r["ms"] / r["calls"], "share_of_step": r["ms"] / total_ms if total_ms else None,
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)"}
     if args.profile_out and rank == 0:
