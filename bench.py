@@ -127,10 +127,42 @@ def run_reference(args):
                              "sample": f"{args.steps} steps of batch {B} (oracle/torch_oracle.py, pinned to the "
                                        "reference scripts; CPU images/s is flat in batch size)"},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    _OUT.emit(json.dumps(line))
+
+
+class _QuietStdout:
+    """Everything written to fd 1 before the result (NCCL prints its version banner there, libraries may print
+    warnings) goes to stderr, so that stdout carries exactly ONE line: the JSON result."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_OUT = None
 
 
 def main():
+    global _OUT
+    with _QuietStdout() as _OUT:
+        _main()
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -293,7 +325,7 @@ def main():
         line["cpu_baseline"] = {"value": cb, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"4 steps of batch {args.cpu_batch} after 2 warm-up on the host CPU "
                                           "(oracle/torch_oracle.py; CPU images/s is flat in batch size)"}
-    print(json.dumps(line))
+    _OUT.emit(json.dumps(line))
 
 
 if __name__ == "__main__":
