@@ -84,6 +84,7 @@ _PROTOS = {
     "eadgan_upsample2x_fwd": [_P, _P, _I, _I, _I, _P],
     "eadgan_upsample2x_bwd": [_P, _P, _I, _I, _I, _P],
     "eadgan_spectral_norm_fwd": [_P, _I, _I, _P, _P, _I, _F, _P, _P, _P, _P],
+    "eadgan_spectral_norm_scale": [_P, _P, _P, C.c_longlong, _P],
     "eadgan_spectral_norm_bwd": [_P, _P, _P, _P, _P, _I, _I, _P, _P, _P],
     "eadgan_bce_fwd": [_P, _P, _L, _P, _P],
     "eadgan_bce_bwd": [_P, _P, _P, _L, _P, _P],

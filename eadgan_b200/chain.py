@@ -107,14 +107,21 @@ def try_run(seq, x):
     params, srcs = [], []
     for st in stages:
         st.conv.__dict__.pop("_eadgan_sn_src", None)
-        for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
-            hook(st.conv, (x,))
+        Fn.sn_skip_scale = True      # W / sigma is materialised only if a SIMT / dense consumer asks for it
+        try:
+            for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
+                hook(st.conv, (x,))
+        finally:
+            Fn.sn_skip_scale = False
         w = st.conv.weight
         # what the tensor-core path packs: the parameter itself (cached until it changes), with sigma applied
         # in the kernel epilogue for spectral-normalised layers; any other weight tensor is packed as is
         sn = st.conv.__dict__.get("_eadgan_sn_src")
         if sn is not None and sn[2] is w and isinstance(sn[0], torch.nn.Parameter):
-            srcs.append((sn[0], sn[1]))
+            srcs.append((sn[0], sn[1], sn[3]))
+        elif sn is not None and sn[3]:
+            Fn.spectral_norm_materialize(sn[0], sn[1], sn[2])   # not packable from weight_orig: needs the values now
+            srcs.append(None)
         elif isinstance(w, torch.nn.Parameter):
             srcs.append((w, None))
         else:
@@ -256,18 +263,27 @@ class _ChainFn(torch.autograd.Function):
             impl = _impl(st, d, last)
             rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl}
             src = srcs[si]
+            lazy = [src is not None and len(src) > 2 and bool(src[2])]
+
+            def wvals(_src=src, _wc=wc, _w=w, _lazy=lazy):
+                """the weight VALUES (W / sigma for spectral-normalised layers), materialised on first use"""
+                if _lazy[0]:
+                    Fn.spectral_norm_materialize(_src[0], _src[1], _w)
+                    _lazy[0] = False
+                return _wc if _wc.data_ptr() == _w.data_ptr() else _w.contiguous()
+            rec["wvals"] = wvals
 
             def packed(direction, ca, _src=src, _wc=wc):
                 """(bf16 GEMM operand, sigma) of this stage's weight for `direction`"""
                 if _src is not None and tuple(_src[0].shape[2:]) == (4, 4):
                     return tc.pack_w_cached(_src[0], direction, ca), _src[1]
-                return tc.pack_w(_wc, None, direction, ca), None
+                return tc.pack_w(wvals(), None, direction, ca), None
             rec["packed"] = packed
 
             def packed_thin(direction, _src=src, _wc=wc):
                 if _src is not None:
                     return tc.thin_pack_w_cached(_src[0], direction), _src[1]
-                return tc.thin_pack_w(_wc, direction), None
+                return tc.thin_pack_w(wvals(), direction), None
             rec["packed_thin"] = packed_thin
             if impl == "thin" and st.kind == "conv":
                 inp = cur
@@ -283,12 +299,12 @@ class _ChainFn(torch.autograd.Function):
                 out = _Buf(tc.thin_dgrad(inp.t, wpk, b, d.c, epi_act[0], epi_act[1], sigma=sg), "ext")
             elif impl == "dense_T":      # 1x1 -> 4x4 ConvTranspose: batch GEMM, scatter epilogue
                 a = tc.pad_rows(cur.t.reshape(d.n, d.k), _r64(d.k))
-                out = _Buf(tc.dense_scatter(a, tc.dense_pack(wc, _r64(d.k), False), b, d.c), "pad")
+                out = _Buf(tc.dense_scatter(a, tc.dense_pack(wvals(), _r64(d.k), False), b, d.c), "pad")
                 inp = cur
                 rec["a"] = a
             elif impl == "dense_C":    # 4x4 -> 1x1 Conv head: batch GEMM, gather prologue
                 inp = _Buf(cur.padded(), "pad")
-                o = tc.dense_gather(inp.t, tc.dense_pack(wc, 32, True), b, d.k)
+                o = tc.dense_gather(inp.t, tc.dense_pack(wvals(), 32, True), b, d.k)
                 out = _Buf(o.view(d.n, d.k, 1, 1), "ext")
             elif impl == "tc":
                 ca = _calloc(d)
@@ -311,7 +327,7 @@ class _ChainFn(torch.autograd.Function):
                     out = _Buf(tc.alloc_padded(out_shape[0], out_shape[2], out_shape[3], cout, dev), "pad")
                 ind, outd = t4(inp.view()), t4(out.view())
                 call("eadgan_conv_fprop" if st.kind == "conv" else "eadgan_conv_dgrad", C.byref(d), C.byref(ind),
-                     ptr(wc), ptr(b), epi_act[0], float(epi_act[1]), C.byref(outd), None, ACT_NONE, 0.0, st_)
+                     ptr(wvals()), ptr(b), epi_act[0], float(epi_act[1]), C.byref(outd), None, ACT_NONE, 0.0, st_)
                 if stats is not None:
                     call("eadgan_bn_stats", C.byref(outd), out_shape[0], cout, out_shape[2], out_shape[3],
                          ptr(stats), st_)
@@ -442,7 +458,7 @@ class _ChainFn(torch.autograd.Function):
                 a = tc.pad_rows(dz.t.reshape(d.n, d.k), 64)
                 dw = tc.dense_wgrad(a, sv["inp"].t, d.k)
                 if need_dx and (si > 0) and (not fuse or sv["inp"].fmt == "pad"):
-                    dx = _Buf(tc.dense_scatter(a, tc.dense_pack(sv["w"], 64, False), None, d.c,
+                    dx = _Buf(tc.dense_scatter(a, tc.dense_pack(sv["wvals"](), 64, False), None, d.c,
                                                mask=sv["inp"].t if fuse else None, mask_act=mask_act,
                                                slope=mask_slope, chan_sums=sums_buf), "pad")
                     sums_used = want_sums
@@ -487,7 +503,7 @@ class _ChainFn(torch.autograd.Function):
                 dzd, dxd = t4(dzv), t4(dx.view())
                 md = t4(sv["inp"].view()) if fuse else None
                 call("eadgan_conv_dgrad" if st.kind == "conv" else "eadgan_conv_fprop", C.byref(d), C.byref(dzd),
-                     ptr(sv["w"]), None, ACT_NONE, 0.0, C.byref(dxd), C.byref(md) if fuse else None, mask_act,
+                     ptr(sv["wvals"]()), None, ACT_NONE, 0.0, C.byref(dxd), C.byref(md) if fuse else None, mask_act,
                      float(mask_slope), st_)
             if need_dx:
                 g, g_masked = dx, fuse

@@ -29,39 +29,50 @@ __global__ void __launch_bounds__(128) sn_wtu_kernel(const float* __restrict__ W
   t[(int64_t)blockIdx.y * cols + j] = acc;   // per-split partial: summed in a fixed order by sn_normalize_kernel
 }
 
-// single block: x = sum over `parts` partial vectors (fixed order: deterministic); out = x / max(||x||, eps).
-// `in` is overwritten with x in its first n entries.
-__global__ void __launch_bounds__(1024) sn_normalize_kernel(float* __restrict__ in, float* __restrict__ out,
-                                                            int n, int parts, float eps) {
+// x = sum over `parts` partial vectors (fixed order: deterministic), stored over the first slab; per-block partial
+// of ||x||^2 -> nrm[block].  Replaces a single-block pass over parts x n floats (24 us at 19 x 8192).
+__global__ void __launch_bounds__(256) sn_vsum_kernel(float* __restrict__ t, int n, int parts, float* __restrict__ nrm) {
   __shared__ float red[32];
-  float s = 0.f;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float x = in[i];
-    for (int p = 1; p < parts; ++p) x += in[(int64_t)p * n + i];
-    in[i] = x;
-    s = fmaf(x, x, s);
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  float x = 0.f;
+  if (i < n) {
+    x = t[i];
+    for (int p = 1; p < parts; ++p) x += t[(int64_t)p * n + i];
+    t[i] = x;
   }
-  s = eg_block_sum(s, red);
-  const float inv = 1.f / fmaxf(sqrtf(s), eps);
-  for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = in[i] * inv;
+  const float s = eg_block_sum(x * x, red);
+  if (threadIdx.x == 0) nrm[blockIdx.x] = s;
 }
 
-// s[i] = sum_j W[i,j] v[j];  one block per row
-__global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ v,
-                                                    float* __restrict__ s, int rows, int cols) {
+// s[i] = sum_j W[i,j] v[j] with v = x / max(||x||, eps) formed on the fly (x: un-normalised W^T u, nrm: the
+// partials of ||x||^2, re-summed by every block in the same order); block i also stores its slice of v.
+// x == nullptr: v is taken as is (no power iteration).  One block per row.
+__global__ void __launch_bounds__(256) sn_wv_kernel(const float* __restrict__ W, const float* __restrict__ x,
+                                                    const float* __restrict__ nrm, int nparts, float eps,
+                                                    float* __restrict__ v, float* __restrict__ s, int rows, int cols) {
   __shared__ float red[32];
   const int i = blockIdx.x;
   const float* wr = W + (int64_t)i * cols;
+  float inv = 1.f;
+  if (x != nullptr) {
+    float q = 0.f;
+    for (int p = 0; p < nparts; ++p) q += nrm[p];
+    inv = 1.f / fmaxf(sqrtf(q), eps);
+    const int chunk = (cols + rows - 1) / rows;
+    for (int j = i * chunk + threadIdx.x; j < min(cols, (i + 1) * chunk); j += blockDim.x) v[j] = x[j] * inv;
+  }
+  const float* src = x != nullptr ? x : v;
   float acc = 0.f;
-  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(v)) & 15) == 0) {
+  if ((cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(wr) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
     for (int j = threadIdx.x; j < (cols >> 2); j += blockDim.x) {
       const float4 a = reinterpret_cast<const float4*>(wr)[j];
-      const float4 b = reinterpret_cast<const float4*>(v)[j];
+      float4 b = reinterpret_cast<const float4*>(src)[j];
+      if (x != nullptr) { b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv; }
       acc = fmaf(a.x, b.x, acc); acc = fmaf(a.y, b.y, acc);
       acc = fmaf(a.z, b.z, acc); acc = fmaf(a.w, b.w, acc);
     }
   } else {
-    for (int j = threadIdx.x; j < cols; j += blockDim.x) acc = fmaf(wr[j], v[j], acc);
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) acc = fmaf(wr[j], x != nullptr ? src[j] * inv : src[j], acc);
   }
   acc = eg_block_sum(acc, red);
   if (threadIdx.x == 0) s[i] = acc;
@@ -170,15 +181,17 @@ extern "C" int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols,
   if (splits < 1) splits = 1;
   const int rpb = (rows + splits - 1) / splits;
   splits = (rows + rpb - 1) / rpb;
-  float* s = scratch;          // [rows]
-  float* t = scratch + rows;   // [splits][cols] partials of W^T u
+  float* s = scratch;                    // [rows]
+  float* nrm = scratch + ((rows + 3) & ~3);   // [ceil(cols/256)] partials of ||W^T u||^2
+  const int nparts = (cols + 255) / 256;
+  float* t = nrm + ((nparts + 3) & ~3);  // [splits][cols] partials of W^T u (16-byte aligned with `scratch`)
   if (do_power_iter) {
     sn_wtu_kernel<<<dim3(col_tiles, splits), 128, 0, st>>>(w_orig, u, t, rows, cols, rpb);
     EG_LAUNCH_CHECK("sn_wtu_kernel");
-    sn_normalize_kernel<<<1, 1024, 0, st>>>(t, v, cols, splits, eps);
-    EG_LAUNCH_CHECK("sn_normalize_kernel");
+    sn_vsum_kernel<<<nparts, 256, 0, st>>>(t, cols, splits, nrm);
+    EG_LAUNCH_CHECK("sn_vsum_kernel");
   }
-  sn_wv_kernel<<<rows, 256, 0, st>>>(w_orig, v, s, rows, cols);
+  sn_wv_kernel<<<rows, 256, 0, st>>>(w_orig, do_power_iter ? t : nullptr, nrm, nparts, eps, v, s, rows, cols);
   EG_LAUNCH_CHECK("sn_wv_kernel");
   sn_sigma_kernel<<<1, 1024, 0, st>>>(s, u, rows, eps, do_power_iter ? 1 : 0, sigma);
   EG_LAUNCH_CHECK("sn_sigma_kernel");
@@ -208,5 +221,15 @@ extern "C" int eadgan_spectral_norm_bwd(const float* dw_sn, const float* w_orig,
 /* floats of scratch the two entry points need (per-split / per-block partial sums live there) */
 extern "C" size_t eadgan_spectral_norm_scratch_floats(int rows, int cols, int backward) {
   if (backward) return (size_t)grid_for((int64_t)rows * cols) + 8;
-  return (size_t)rows + (size_t)((rows + 15) / 16 + 1) * (size_t)cols + 8;
+  return (size_t)((rows + 3) & ~3) + (size_t)(((cols + 255) / 256 + 3) & ~3) + (size_t)((rows + 15) / 16 + 1) * (size_t)cols + 8;
+}
+
+/* W_sn = W / sigma on its own: the forward entry point skips it when w_sn == NULL (the tcgen05 chain applies
+ * 1/sigma in the conv epilogue); a consumer that does need the normalised weight materialises it with this. */
+extern "C" int eadgan_spectral_norm_scale(const float* w_orig, const float* sigma, float* w_sn, long long n,
+                                          void* stream) {
+  EG_REQUIRE(w_orig && sigma && w_sn && n > 0, EADGAN_ERR_INVALID, "spectral_norm_scale: bad arguments");
+  sn_scale_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(w_orig, sigma, w_sn, n);
+  EG_LAUNCH_CHECK("sn_scale_kernel");
+  return 0;
 }

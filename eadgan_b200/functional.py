@@ -362,8 +362,11 @@ class _SpectralNormFn(torch.autograd.Function):
         w_sn = torch.empty_like(w)
         scratch = torch.empty(L.lib().eadgan_spectral_norm_scratch_floats(rows, cols, 0), device=w.device,
                               dtype=torch.float32)
+        # sn_skip_scale (set by the bf16 chain executor around the pre-forward hooks): W / sigma is NOT written --
+        # the chain packs weight_orig and applies 1/sigma in the conv epilogue; spectral_norm_materialize() fills
+        # w_sn later if some consumer needs its values
         call("eadgan_spectral_norm_fwd", ptr(w), rows, cols, ptr(u), ptr(v), 1 if do_power_iter else 0,
-             float(eps), ptr(sigma), ptr(w_sn), ptr(scratch), stream())
+             float(eps), ptr(sigma), None if sn_skip_scale else ptr(w_sn), ptr(scratch), stream())
         ctx.mark_non_differentiable(sigma)
         # u, v are cloned exactly like the reference does, so later in-place power
         # iterations (6 per CelebA step) do not corrupt this graph's backward
@@ -382,6 +385,14 @@ class _SpectralNormFn(torch.autograd.Function):
         call("eadgan_spectral_norm_bwd", ptr(dw_sn), ptr(w), ptr(u), ptr(v), ptr(sigma), rows, cols, ptr(dw),
              ptr(scratch), stream())
         return dw, None, None, None, None
+
+
+sn_skip_scale = False
+
+
+def spectral_norm_materialize(w_orig, sigma, w_sn):
+    """w_sn <- w_orig / sigma (for a forward that ran with sn_skip_scale)."""
+    call("eadgan_spectral_norm_scale", ptr(w_orig.detach().contiguous()), ptr(sigma), ptr(w_sn), w_sn.numel(), stream())
 
 
 def spectral_norm_weight(w_orig, u, v, do_power_iter, eps):

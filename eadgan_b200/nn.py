@@ -226,7 +226,7 @@ class SpectralNorm(_tsn.SpectralNorm):
         module._eadgan_sigma = sigma
         # (weight_orig, sigma, the tensor about to become module.weight): lets the bf16 chain pack weight_orig
         # once per optimiser step and apply 1/sigma in the conv epilogue (eadgan_b200.chain.try_run)
-        module.__dict__["_eadgan_sn_src"] = (weight, sigma, w_sn)
+        module.__dict__["_eadgan_sn_src"] = (weight, sigma, w_sn, Fn.sn_skip_scale)
         return w_sn
 
 

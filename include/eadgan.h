@@ -285,6 +285,8 @@ int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols, float* u, 
                              int do_power_iter, float eps, float* sigma, float* w_sn,
                              float* scratch, void* stream);
 /* dW_orig = dW/sigma - (<dW, W_orig>/sigma^2) u v^T      */
+/* W_sn = W / sigma alone (eadgan_spectral_norm_fwd skips it when w_sn == NULL) */
+int eadgan_spectral_norm_scale(const float* w_orig, const float* sigma, float* w_sn, long long n, void* stream);
 int eadgan_spectral_norm_bwd(const float* dw_sn, const float* w_orig, const float* u,
                              const float* v, const float* sigma, int rows, int cols,
                              float* dw_orig, float* scratch, void* stream);
