@@ -188,8 +188,8 @@ def _tc_ok(d, direction):
     if direction == "fprop":
         return d.k % 32 == 0 and d.q <= 128
     if direction == "dgrad":
-        return d.k % 64 == 0 and d.q <= 128
-    return (d.k % 128 == 0 or d.k == 64) and d.q <= 64  # wgrad
+        return (d.k % 64 == 0 or d.k == 32) and d.q <= 128
+    return d.k % 32 == 0 and d.q <= 64  # wgrad
 
 
 def _thin_ok(d, direction):
@@ -201,8 +201,8 @@ def _thin_ok(d, direction):
     if direction == "fprop":
         return d.k % 32 == 0 and d.q <= 128
     if direction == "dgrad":      # GEMM + col2im epilogue: 32-wide small map, <= 3 image channels
-        return d.k % 64 == 0 and d.q == 32 and d.c <= 3
-    return (d.k % 128 == 0 or d.k == 64) and d.q <= 64  # wgrad
+        return (d.k % 64 == 0 or d.k == 32) and d.q == 32 and d.c <= 3
+    return d.k % 32 == 0 and d.q <= 64  # wgrad
 
 
 def _impl(st, d, last):

@@ -384,7 +384,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
               }
             }
           }
-          tma_load_2d(sb, &map_b, &full_bar[stage], kbg * BLOCK_K,
+          // dgrad: tap t's weights start at column t * K_ch (= kb * 64 whenever K_ch is a multiple of 64; for
+          // K_ch = 32 the box also covers 32 columns of the next tap, multiplied by the zero-filled half of A)
+          tma_load_2d(sb, &map_b, &full_bar[stage], P.mode == MODE_DGRAD ? t * P.K_ch + qi * BLOCK_K : kbg * BLOCK_K,
                       (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
@@ -1107,7 +1109,8 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   if (int e = check_tc(d, "tc_dgrad")) return e;
   EG_REQUIRE(dy_pad && w_packed && dx, EADGAN_ERR_INVALID, "tc_dgrad: NULL pointer");
   const int p = d->h / 2, q = d->w / 2;
-  EG_REQUIRE(d->k % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: k=%d must be a multiple of 64", d->k);
+  // k = 32: the 64-channel TMA boxes run past the tensor and are zero-filled (half of each k block is idle)
+  EG_REQUIRE(d->k % 64 == 0 || d->k == 32, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: k=%d must be 32 or a multiple of 64", d->k);
   TcParams P{};
   P.mode = MODE_DGRAD; P.n = d->n; P.p = p; P.q = q;
   EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
@@ -1115,7 +1118,7 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
   const int bn = pick_bn_tiles(d->c, 4 * m_tiles);
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
-  P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = d->k / 64; P.nkb = 4 * P.qblocks;
+  P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = (d->k + 63) / 64; P.nkb = 4 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
   P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.sigma = sigma;
@@ -1134,7 +1137,8 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
 namespace {
 int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
   const int p = d->h / 2, q = d->w / 2;
-  EG_REQUIRE(d->k % 128 == 0 || d->k == 64, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: k=%d must be 64 or a multiple of 128", d->k);
+  // dy channel boxes past k are zero-filled by TMA and the matching partial rows are never read
+  EG_REQUIRE(d->k % 32 == 0, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: k=%d must be a multiple of 32", d->k);
   EG_REQUIRE((2 * d->c) % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: c=%d must be a multiple of 32", d->c);
   P->n = d->n; P->p = p; P->q = q; P->k = d->k; P->c = d->c;
   EG_REQUIRE(pick_tile(p, q, 64, &P->Tw, &P->Th, &P->Tb) == 0, EADGAN_ERR_UNSUPPORTED,
@@ -1679,8 +1683,7 @@ extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, 
 namespace {
 int thin_wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* splits) {
   const int p = d->h / 2, q = d->w / 2;
-  EG_REQUIRE(d->k % 128 == 0 || d->k == 64, EADGAN_ERR_UNSUPPORTED, "tc_thin_wgrad: k=%d must be 64 or a multiple of 128",
-             d->k);
+  EG_REQUIRE(d->k % 32 == 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_wgrad: k=%d must be a multiple of 32", d->k);
   P->n = d->n; P->p = p; P->q = q; P->k = d->k; P->c = 4; P->thin = 1;
   EG_REQUIRE(pick_tile(p, q, 64, &P->Tw, &P->Th, &P->Tb) == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_thin_wgrad: small map %dx%d must be a power of two <= 64 wide", p, q);
@@ -1738,10 +1741,10 @@ extern "C" int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad,
   const int p = d->h / 2, q = d->w / 2;
   EG_REQUIRE(q == 32 && p >= 2 && p % 2 == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_thin_dgrad: the small map must be 32 wide with an even number of rows (got %dx%d)", p, q);
-  EG_REQUIRE(d->k % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_dgrad: k=%d must be a multiple of 64", d->k);
+  EG_REQUIRE(d->k % 64 == 0 || d->k == 32, EADGAN_ERR_UNSUPPORTED, "tc_thin_dgrad: k=%d must be 32 or a multiple of 64", d->k);
   EG_REQUIRE(d->c <= 3, EADGAN_ERR_UNSUPPORTED, "tc_thin_dgrad: at most 3 image channels");
   ThinDgParams P{};
-  P.n = d->n; P.p = p; P.nkb = d->k / 64; P.tiles_per_img = p / 2; P.c_real = d->c; P.act = d->act; P.slope = d->slope;
+  P.n = d->n; P.p = p; P.nkb = (d->k + 63) / 64; P.tiles_per_img = p / 2; P.c_real = d->c; P.act = d->act; P.slope = d->slope;
   P.bias = bias; P.sigma = sigma; P.out = out;
   CUtensorMap ma, mb;
   if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, 32, 4, 1)) return e;
