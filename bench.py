@@ -258,13 +258,20 @@ def _main():
         # graph: the replay wrapper copies the pinned host tensors straight into its static device inputs
         return hb if use_graph else [t.to(dev, non_blocking=True) for t in hb]
 
+    # graph: while replay i runs, the pinned host batch of step i + 1 is copied on a copy stream (every step's H2D
+    # copy and the D2H read of its losses are inside the timed region; only the very first batch is staged before)
+    def e2e_step(i):
+        if use_graph:
+            return step(*host[i % R], prefetch=host[(i + 1) % R])
+        return step(*from_host(host[i % R]))
+
     for i in range(2):
-        step(*from_host(host[i % R]))
+        e2e_step(i)
     barrier()
     d2h_bytes = 0
     e0.record()
     for i in range(args.steps):
-        out = step(*from_host(host[i % R]))
+        out = e2e_step(2 + i)
         vals = torch.stack([out["g_loss"], out["d_loss"], out["info_loss"]]).cpu()
         d2h_bytes = vals.numel() * vals.element_size()
     e1.record()

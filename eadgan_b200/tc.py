@@ -18,6 +18,7 @@ from ._lib import ACT_NONE, call, ptr, stream, t4
 # temporaries); reuse is stream-ordered exactly like the caching allocator's.
 _pool = {}
 _pool_enabled = True
+capture_births = None   # list while a CUDA-graph capture is running (eadgan_b200.graph): buffers first created inside it
 
 
 def _recycle(key, base):
@@ -33,7 +34,15 @@ def alloc_padded(n, h, w, c, device, zero_interior=False, c_real=None):
         return torch.zeros(shape, device=device, dtype=torch.bfloat16)
     key = (shape, c_real or c, str(device))
     free = _pool.get(key)
-    base = free.pop() if free else torch.zeros(shape, device=device, dtype=torch.bfloat16)
+    if free:
+        base = free.pop()
+    else:
+        base = torch.zeros(shape, device=device, dtype=torch.bfloat16)
+        if capture_births is not None:
+            # created during capture: the zero fill is only RECORDED, the memory holds garbage until the graph's first
+            # replay.  GraphedStep zeroes these for real right after the capture, because the buffer now circulates
+            # in the pool and eager code (or another capture) may pick it up before this graph ever runs.
+            capture_births.append(base)
     t = base.view(shape)
     weakref.finalize(t, _recycle, key, base)
     return t

@@ -46,3 +46,26 @@ def test_graphed_step_matches_eager(cuda, prec):
     assert st["step"] == W + K
     assert int(graphed.opt_G._step_dev) == W + K
     assert gs.kernels_per_replay > 100
+
+
+def test_prefetch_pipeline_gives_the_same_steps(cuda):
+    """GraphedStep(..., prefetch=next batch): the next step's host->device copy runs on a copy stream during the
+    current replay; results must equal feeding the same batches without the pipeline."""
+    os.environ["EADGAN_PRECISION"] = "bf16"
+    from eadgan_b200.graph import GraphedStep
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle.torch_oracle import sample_celeba, synth_celeba_images
+    B = 16
+
+    def host_batch(i):
+        d = sample_celeba(np.random.RandomState(20 + i), B)
+        return [t.contiguous().pin_memory() for t in (synth_celeba_images(B, i), d["z"], d["code"], d["labels"])]
+
+    batches = [host_batch(i) for i in range(4)]
+    dev0 = [t.to(cuda) for t in batches[0]]
+    plain = GraphedStep(CelebAStep(seed=0, device=cuda), dev0, warmup=1)
+    piped = GraphedStep(CelebAStep(seed=0, device=cuda), dev0, warmup=1)
+    for i in range(4):
+        a = {k: float(v) for k, v in plain(*batches[i]).items()}
+        b = {k: float(v) for k, v in piped(*batches[i], prefetch=batches[(i + 1) % 4]).items()}
+        assert a == b, (i, a, b)
