@@ -95,6 +95,57 @@ def _plan(seq):
     return cached[1]
 
 
+_sn_streams = {}
+
+
+def prefetch_spectral_norm(seq, count=1):
+    """Run the spectral-norm power iterations of the NEXT ``count`` forwards of ``seq`` now, on a side stream.
+
+    The legacy spectral_norm hook depends only on weight_orig and the u / v buffers -- not on the activations --
+    so a step driver that knows how many forwards of a network follow before its weights change can issue their
+    power iterations early; they then overlap whatever the main stream is doing (the other network's forward, a
+    backward pass) instead of sitting, 4 small launches per layer, on the critical path in front of every conv
+    stack.  Results are queued per module in forward order; ``try_run`` consumes them (and waits on the side
+    stream's event) instead of calling the hooks.  Same arithmetic, same order of u / v updates."""
+    if precision() != "bf16":
+        return
+    stages = _plan(seq)
+    if stages is None:
+        return
+    convs = [st.conv for st in stages if st.conv._forward_pre_hooks]
+    if not convs:
+        return
+    w0 = getattr(convs[0], "weight_orig", None)
+    if w0 is None or not w0.is_cuda:
+        return
+    cur = torch.cuda.current_stream()
+    side = _sn_streams.get(w0.device)
+    if side is None:
+        side = _sn_streams[w0.device] = torch.cuda.Stream(device=w0.device)
+    side.wait_stream(cur)          # the weights (last optimiser step) and every earlier u / v update are visible
+    with torch.cuda.stream(side):
+        for _ in range(count):
+            done = []
+            Fn.sn_skip_scale = True
+            try:
+                for conv in convs:
+                    conv.__dict__.pop("_eadgan_sn_src", None)
+                    for hook in conv._forward_pre_hooks.values():
+                        hook(conv, (None,))
+                    done.append((conv.weight, conv.__dict__.get("_eadgan_sn_src")))
+            finally:
+                Fn.sn_skip_scale = False
+            ev = torch.cuda.Event()
+            ev.record(side)
+            for conv, entry in zip(convs, done):
+                conv.__dict__.setdefault("_eadgan_sn_queue", []).append((entry, ev))
+
+
+def clear_prefetch(seq):
+    for m in seq._modules.values():
+        m.__dict__.pop("_eadgan_sn_queue", None)
+
+
 def try_run(seq, x):
     """Returns the Sequential's output, or None when the chain path does not apply."""
     if precision() != "bf16" or not torch.is_tensor(x) or not x.is_cuda or x.dim() != 4 or x.dtype != torch.float32:
@@ -106,13 +157,28 @@ def try_run(seq, x):
         return None  # eval-mode BN: per-op path
     params, srcs = [], []
     for st in stages:
-        st.conv.__dict__.pop("_eadgan_sn_src", None)
-        Fn.sn_skip_scale = True      # W / sigma is materialised only if a SIMT / dense consumer asks for it
-        try:
-            for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
-                hook(st.conv, (x,))
-        finally:
-            Fn.sn_skip_scale = False
+        queue = st.conv.__dict__.get("_eadgan_sn_queue")
+        if queue:
+            # this forward's power iteration was issued ahead of time (prefetch_spectral_norm): adopt its results
+            (w_pre, sn_pre), ev = queue.pop(0)
+            cur = torch.cuda.current_stream()
+            cur.wait_event(ev)
+            for t in (w_pre,) + (tuple(sn_pre[1:3]) if sn_pre is not None else ()):
+                if torch.is_tensor(t):
+                    t.record_stream(cur)
+            setattr(st.conv, "weight", w_pre)
+            if sn_pre is not None:
+                st.conv.__dict__["_eadgan_sn_src"] = sn_pre
+            else:
+                st.conv.__dict__.pop("_eadgan_sn_src", None)
+        else:
+            st.conv.__dict__.pop("_eadgan_sn_src", None)
+            Fn.sn_skip_scale = True      # W / sigma is materialised only if a SIMT / dense consumer asks for it
+            try:
+                for hook in st.conv._forward_pre_hooks.values():  # legacy spectral_norm lives here
+                    hook(st.conv, (x,))
+            finally:
+                Fn.sn_skip_scale = False
         w = st.conv.weight
         # what the tensor-core path packs: the parameter itself (cached until it changes), with sigma applied
         # in the kernel epilogue for spectral-normalised layers; any other weight tensor is packed as is

@@ -53,6 +53,7 @@ class _InvalidateOnLoad:
     def _load_from_state_dict(self, *args, **kwargs):
         from . import _lib
         _lib.bump_weights_epoch()
+        self.__dict__.pop("_eadgan_sn_queue", None)   # prefetched spectral-norm results belong to the old state
         return super()._load_from_state_dict(*args, **kwargs)
 
 

@@ -12,7 +12,7 @@ import itertools
 
 import torch
 
-from .. import affine, functional as Fn
+from .. import affine, chain, functional as Fn
 from .. import nn as nn
 from ..optim import Adam
 from .._lib import ACT_SIGMOID
@@ -96,6 +96,11 @@ class CelebAStep:
         onehot.scatter_(1, labels.view(-1, 1), 1.0)
         scaled = affine.stn(imgs, affine.celeba_matrix(code[:, :5])[:, 0:2])
 
+        # D's weights do not change until opt_D.step(): the power iterations of its next three forwards (D(gen) below,
+        # then the two of phase D) depend only on the weights and on u / v, so they are issued now, on a side stream,
+        # and overlap G's forward instead of preceding every D conv stack on the critical path
+        chain.prefetch_spectral_norm(D.main, 3)
+
         # phase G -- :334-345
         self.opt_G.zero_grad()
         gen = G(z, onehot, code)
@@ -119,6 +124,7 @@ class CelebAStep:
         self._after(self.opt_D, record)
         if after_phase is not None:
             after_phase(1)
+        chain.prefetch_spectral_norm(D.main, 3)     # the info phase's three D forwards (weights fixed until opt_info.step)
 
         # phase info -- :375-401
         self.opt_info.zero_grad()

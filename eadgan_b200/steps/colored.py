@@ -15,7 +15,7 @@ import itertools
 
 import torch
 
-from .. import affine, functional as Fn
+from .. import affine, chain, functional as Fn
 from .. import nn as nn
 from ..optim import Adam
 from .dsprites import Discriminator, DSpritesStep, Encoder, Encoder_pxy, Generator, N_CLASSES
@@ -72,6 +72,9 @@ class ColoredDSpritesStep(DSpritesStep):
             o.scatter_(1, labels.view(-1, 1), 1.0)
             return o
 
+        chain.prefetch_spectral_norm(D.conv_block, 2)      # see steps/dsprites.py
+        chain.prefetch_spectral_norm(E.conv_block, 3)
+
         # phase D -- rp_color.py:397-441
         align_img = self._aligned(img)
         trans_img = self._distorted(align_img, code_d)
@@ -86,6 +89,7 @@ class ColoredDSpritesStep(DSpritesStep):
         self._after(self.opt_D, record)
         if after_phase is not None:
             after_phase(0)
+        chain.prefetch_spectral_norm(D.conv_block, 1)      # D(gen) of the info phase
 
         # phase info -- rp_color.py:444-516
         lab = onehot(labels_info)

@@ -16,7 +16,7 @@ import itertools
 
 import torch
 
-from .. import affine, functional as Fn
+from .. import affine, chain, functional as Fn
 from .. import nn as nn
 from ..optim import Adam
 from .._lib import ACT_SIGMOID
@@ -137,6 +137,11 @@ class DSpritesStep:
             o.scatter_(1, labels.view(-1, 1), 1.0)
             return o
 
+        # spectral-norm power iterations of the coming forwards, issued early on a side stream (they depend only on
+        # weights that stay fixed until the owning optimiser steps): D twice in phase D, E three times in phase info
+        chain.prefetch_spectral_norm(D.conv_block, 2)
+        chain.prefetch_spectral_norm(E.conv_block, 3)
+
         # phase D -- rp.py:379-419
         align_img = self._aligned(img)
         trans_img = affine.stn(align_img, affine.dsprites_matrix23(code_d))
@@ -151,6 +156,7 @@ class DSpritesStep:
         self._after(self.opt_D, record)
         if after_phase is not None:
             after_phase(0)
+        chain.prefetch_spectral_norm(D.conv_block, 1)      # D(gen) of the info phase
 
         # phase info -- rp.py:424-482
         lab = onehot(labels_info)
