@@ -77,8 +77,13 @@ if graph_mode:
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     dist.barrier()
-    dist.destroy_process_group()
-    sys.exit(0 if int(flag.item()) else 1)
+    code = 0 if int(flag.item()) else 1
+    torch.cuda.synchronize()
+    # The captured graph holds NCCL kernels of this communicator: tearing the process group down while the graph
+    # is alive blocks in NCCL.  Leave without destroying the group (the process is about to exit anyway).
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)
 
 rec = []
 # record the REDUCED gradients: snapshot inside Adam.step via the dp.reduce() return value
