@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(128) sn_wtu_kernel(const float* __restrict__ W
     acc = fmaf(a2, u[i + 2], acc); acc = fmaf(a3, u[i + 3], acc);
   }
   for (; i < r1; ++i) acc = fmaf(W[(int64_t)i * cols + j], u[i], acc);
-  t[(int64_t)blockIdx.y * cols + j] = acc;   // per-split partial: summed in a fixed order by sn_normalize_kernel
+  t[(int64_t)blockIdx.y * cols + j] = acc;   // per-split partial: summed in a fixed order by sn_vsum_kernel
 }
 
 // x = sum over `parts` partial vectors (fixed order: deterministic), stored over the first slab; per-block partial
