@@ -339,14 +339,14 @@ class _ChainFn(torch.autograd.Function):
                 return _wc if _wc.data_ptr() == _w.data_ptr() else _w.contiguous()
             rec["wvals"] = wvals
 
-            def packed(direction, ca, _src=src, _wc=wc):
+            def packed(direction, ca, _src=src):
                 """(bf16 GEMM operand, sigma) of this stage's weight for `direction`"""
                 if _src is not None and tuple(_src[0].shape[2:]) == (4, 4):
                     return tc.pack_w_cached(_src[0], direction, ca), _src[1]
                 return tc.pack_w(wvals(), None, direction, ca), None
             rec["packed"] = packed
 
-            def packed_thin(direction, _src=src, _wc=wc):
+            def packed_thin(direction, _src=src):
                 if _src is not None:
                     return tc.thin_pack_w_cached(_src[0], direction), _src[1]
                 return tc.thin_pack_w(wvals(), direction), None

@@ -323,3 +323,37 @@ def test_sass_is_blackwell_native():
     sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
+
+
+def test_chain_plans_route_every_celeba_and_dsprites_layer_to_a_tensor_core_kernel():
+    """host logic of the bf16 chain executor (no kernels run): which kernel family each layer of the reference
+    networks is planned on.  Guards the geometry rules (_tc_ok / _thin_ok / dense) against regressions that would
+    silently push a hot layer back to the SIMT kernels."""
+    from eadgan_b200 import chain
+    from eadgan_b200.steps import celeba, dsprites
+
+    def impls(seq, in_shape):
+        stages = chain._plan(seq)
+        assert stages is not None
+        out, shape = [], in_shape
+        for i, st in enumerate(stages):
+            d = chain._geom(st, shape)
+            out.append(chain._impl(st, d, i == len(stages) - 1))
+            shape = (d.n, d.k, d.p, d.q) if st.kind == "conv" else (d.n, d.c, d.h, d.w)
+        return out, shape
+
+    torch.manual_seed(0)
+    got, shape = impls(celeba.Generator().conv_blocks, (8, 218, 1, 1))
+    assert got == ["dense_T", "tc", "tc", "tc", "thin"] and shape == (8, 3, 64, 64)
+    got, shape = impls(celeba.Discriminator().main, (8, 3, 64, 64))
+    assert got == ["thin", "tc", "tc", "tc", "dense_C"] and shape == (8, 19, 1, 1)
+    for ch in (1, 3):
+        got, shape = impls(dsprites.Generator(ch, 4 if ch == 1 else 7).conv_block, (8, 64, 4, 4))
+        assert got == ["tc", "tc", "tc", "thin"] and shape == (8, ch, 64, 64)
+        got, shape = impls(dsprites.Discriminator(ch).conv_block, (8, ch, 64, 64))
+        assert got == ["thin", "tc", "tc", "tc"] and shape == (8, 64, 4, 4)
+    # backward directions of the 32-channel dSprites layers (k = 32: zero-filled 64-wide TMA boxes)
+    d32 = chain._geom(chain._plan(dsprites.Discriminator(1).conv_block)[1], (8, 32, 32, 32))
+    assert chain._tc_ok(d32, "dgrad") and chain._tc_ok(d32, "wgrad")
+    d0 = chain._geom(chain._plan(dsprites.Discriminator(1).conv_block)[0], (8, 1, 64, 64))
+    assert chain._thin_ok(d0, "dgrad") and chain._thin_ok(d0, "wgrad")

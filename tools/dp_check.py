@@ -59,7 +59,7 @@ if graph_mode:
         Fn.set_allreduce(None, 1)
         ref = CelebAStep(seed=0, device=dev)
         ref(*full)
-        tol = 2e-3 if prec == "fp32" else 3e-2   # Adam's lr*sign(g) noise after 1-2 updates, see above
+        tol = 5e-3 if prec == "fp32" else 3e-2   # Adam's lr*sign(g) noise after 1-2 updates, see above
         for i, batch in enumerate((full2, full)):
             o = ref(*batch)
             v = torch.stack([o["g_loss"], o["d_loss"], o["info_loss"]]).double()
