@@ -320,7 +320,10 @@ def _main():
                    "weights": "random-init seed 0"},
         "clocks": clocks,
         "e2e": {"value": ips_e2e, "unit": "images/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "input_pipeline": ("step i+1's pinned host batch is copied on a copy stream while step i's graph replays; "
+                                   "every step's H2D copy and loss read-back are inside the timed region") if use_graph
+                else "synchronous H2D copy in front of every step"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "step_tensor_frac": {"achieved_tflops": GFLOP_PER_IMG * 1e9 * ips / 1e12,
