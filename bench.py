@@ -300,6 +300,17 @@ def _main():
                 "kernel": name, "launches": r["calls"],
                 "avg_launch_ms": r["ms"] / r["calls"], "share_of_step": r["ms"] / total_ms if total_ms else None,
                 "peak_source": pk["src"] + ", sustained bf16 (kernel timed inside a long step)"}
+    # supplementary HBM-bound roofline: the fused multi-tensor Adam, 28 B per parameter update (read p, g, m, v;
+    # write p, m, v), all three optimiser steps of the iteration
+    roof_hbm = None
+    adam = prof.get("eadgan_adam_step")
+    if adam and adam["ms"] > 0:
+        n_updates = sum(p.numel() for o in eager_step.optimizers() for g in o.param_groups for p in g["params"]
+                        if p.grad is not None)
+        gbs = 28.0 * n_updates / (adam["ms"] * 1e-3) / 1e9
+        roof_hbm = {"bound": "hbm", "kernel": "eadgan_adam_step", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": gbs / pk["hbm"], "algorithmic_bytes_per_step": 28.0 * n_updates, "launches": adam["calls"],
+                    "peak_source": pk["src"]}
     if args.profile_out and rank == 0:
         with open(args.profile_out, "w") as f:
             json.dump({"batch_per_gpu": B, "precision": precision, "step_ms_sum": total_ms,
@@ -326,6 +337,7 @@ def _main():
                 else "synchronous H2D copy in front of every step"},
         "gpu_launches": int(launches),
         "roofline": roof,
+        "roofline_hbm": roof_hbm,
         "step_tensor_frac": {"achieved_tflops": GFLOP_PER_IMG * 1e9 * ips / 1e12,
                              "peak_tflops": pk["tf_sust"] * world, "frac": GFLOP_PER_IMG * 1e9 * ips / 1e12 / (pk["tf_sust"] * world)},
         "losses_last_step": losses,
