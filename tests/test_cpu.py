@@ -357,3 +357,37 @@ def test_chain_plans_route_every_celeba_and_dsprites_layer_to_a_tensor_core_kern
     assert chain._tc_ok(d32, "dgrad") and chain._tc_ok(d32, "wgrad")
     d0 = chain._geom(chain._plan(dsprites.Discriminator(1).conv_block)[0], (8, 1, 64, 64))
     assert chain._thin_ok(d0, "dgrad") and chain._thin_ok(d0, "wgrad")
+
+
+def test_header_is_plain_c():
+    """the drop-in boundary is a C ABI: include/eadgan.h must compile as C (no C++-isms, no torch types)"""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        src = os.path.join(tmp, "abi.c")
+        with open(src, "w") as f:
+            f.write('#include "eadgan.h"\nint main(void) { return (int)sizeof(eadgan_tc_desc) == 0; }\n')
+        r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), src],
+                           capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_reference_arm_prints_one_json_line():
+    """bench.py --impl reference: the reference CPU path timed on the host cores; stdout carries exactly ONE JSON line
+    with the driver's keys (a bounded sample: 1 step of batch 2 here)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-batch", "2"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
