@@ -14,9 +14,10 @@ def main():
         print(__doc__)
         raise SystemExit(2)
     script = os.path.abspath(sys.argv[1])
-    from . import parallel, patch
+    from . import parallel
+    from .patch import patch as apply_patch   # NB: the package re-exports the FUNCTION as eadgan_b200.patch
     parallel.init_from_env()
-    patch.patch()
+    apply_patch()
     sys.argv = [script] + sys.argv[2:]
     sys.path.insert(0, os.path.dirname(script))
     runpy.run_path(script, run_name="__main__")

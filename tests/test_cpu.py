@@ -391,3 +391,27 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "images/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_run_module_patches_before_running_the_script(tmp_path):
+    """python -m eadgan_b200.run <script>: the script sees the replacement classes under the stock torch names
+    (CPU: only the rebinding is checked, no kernel runs).  Regression test: the package re-exports the function
+    ``patch``, which shadowed the submodule inside run.py."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "probe.py"
+    script.write_text(
+        "import sys, torch, torch.nn as nn, torch.nn.functional as F\n"
+        "from torch.nn.utils import spectral_norm\n"
+        "names = [nn.Conv2d.__module__, nn.Sequential.__module__, torch.optim.Adam.__module__, spectral_norm.__module__,\n"
+        "         F.sigmoid.__module__, sys.argv[1]]\n"
+        "print('PROBE', *names)\n")
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "eadgan_b200.run", str(script), "--flag"], capture_output=True, text=True,
+                       timeout=300, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = [ln for ln in r.stdout.splitlines() if ln.startswith("PROBE")][0].split()[1:]
+    assert line == ["eadgan_b200.nn", "eadgan_b200.nn", "eadgan_b200.optim", "eadgan_b200.nn", "eadgan_b200.patch", "--flag"]
+    r = subprocess.run([sys.executable, "-m", "eadgan_b200.run"], capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 2
