@@ -415,3 +415,26 @@ def test_run_module_patches_before_running_the_script(tmp_path):
     assert line == ["eadgan_b200.nn", "eadgan_b200.nn", "eadgan_b200.optim", "eadgan_b200.nn", "eadgan_b200.patch", "--flag"]
     r = subprocess.run([sys.executable, "-m", "eadgan_b200.run"], capture_output=True, text=True, timeout=300, env=env)
     assert r.returncode == 2
+
+
+@pytest.mark.parametrize("c,k", [(3, 8), (1, 5), (4, 6)])
+def test_thin_layer_layout_algebra(c, k):
+    """oracle/thin_layout.py (numpy restatement of the thin kernels' data layout: row-expanded image buffer,
+    (kx, ky, c) patch order, weight packs, col2im ownership rule) against torch's conv2d / conv_transpose2d in fp64."""
+    import torch.nn.functional as TF
+    from oracle import thin_layout as T
+    rs = np.random.RandomState(7)
+    x = rs.randn(2, c, 8, 12)
+    w = rs.randn(k, c, 4, 4)
+    dy = rs.randn(2, k, 4, 6)
+    xt, wt, dyt = (torch.tensor(a) for a in (x, w, dy))
+    r = T.expand(x)
+    assert r.shape == (2, 4, 14, 4, 4)
+    assert np.array_equal(r[:, 1, 3, 2, :c], x[:, :, 2 * 1 + 2 - 1, 3 - 1])            # R[n][oy][X][ky][c] = Xpad[2 oy + ky][X]
+    assert np.abs(T.fprop(x, w) - TF.conv2d(xt, wt, stride=2, padding=1).numpy()).max() < 1e-12
+    wref = torch.zeros_like(wt, requires_grad=True)
+    TF.conv2d(xt, wref, stride=2, padding=1).backward(dyt)
+    assert np.abs(T.wgrad(x, dy) - wref.grad.numpy()).max() < 1e-12
+    if c <= 3:
+        ref = TF.conv_transpose2d(dyt, wt, stride=2, padding=1).numpy()                  # weight read as [Cin = k, Cout = c]
+        assert np.abs(T.dgrad(dy, w) - ref).max() < 1e-12
