@@ -438,3 +438,18 @@ def test_thin_layer_layout_algebra(c, k):
     if c <= 3:
         ref = TF.conv_transpose2d(dyt, wt, stride=2, padding=1).numpy()                  # weight read as [Cin = k, Cout = c]
         assert np.abs(T.dgrad(dy, w) - ref).max() < 1e-12
+
+
+def test_tc_operand_layout_algebra():
+    """oracle/tc_layout.py (numpy restatement of the wide tcgen05 kernels' operand layouts: (a, b, dy, dx, c) K order of
+    the space-to-depth fprop, parity decomposition + Wd pack of dgrad, wgrad column permutation) vs torch in fp64."""
+    import torch.nn.functional as TF
+    from oracle import tc_layout as T
+    rs = np.random.RandomState(3)
+    x, w, dy = rs.randn(2, 5, 8, 12), rs.randn(7, 5, 4, 4), rs.randn(2, 7, 4, 6)
+    xt, wt, dyt = (torch.tensor(a) for a in (x, w, dy))
+    assert np.abs(T.fprop(x, w) - TF.conv2d(xt, wt, stride=2, padding=1).numpy()).max() < 1e-12
+    wref = torch.zeros_like(wt, requires_grad=True)
+    TF.conv2d(xt, wref, stride=2, padding=1).backward(dyt)
+    assert np.abs(T.wgrad(x, dy) - wref.grad.numpy()).max() < 1e-12
+    assert np.abs(T.dgrad(dy, w) - TF.conv_transpose2d(dyt, wt, stride=2, padding=1).numpy()).max() < 1e-12
