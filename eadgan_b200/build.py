@@ -25,5 +25,23 @@ def build(force=False, verbose=False):
     return out
 
 
+def build_experimental(force=False):
+    """csrc/experimental/*.cu are NOT part of libeadgan.so (nothing in the product loads them); they are compiled
+    here only so that the build check covers every CUDA source in the tree."""
+    csrc = os.path.join(HERE, "csrc", "experimental")
+    outs = []
+    for name in sorted(os.listdir(csrc)) if os.path.isdir(csrc) else []:
+        if not name.endswith(".cu"):
+            continue
+        src = os.path.join(csrc, name)
+        out = os.path.join(HERE, "lib", "libeadgan_x_" + name[:-3] + ".so")
+        if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+                            "-Xcompiler", "-fPIC", "-shared", src, "-o", out], check=True)
+        outs.append(out)
+    return outs
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

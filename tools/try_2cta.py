@@ -16,7 +16,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 SRC = os.path.join(ROOT, "eadgan_b200", "csrc", "experimental", "tc_gemm_2cta.cu")
-OUT = os.path.join(ROOT, "eadgan_b200", "lib", "libeadgan_x2cta.so")
+OUT = os.path.join(ROOT, "eadgan_b200", "lib", "libeadgan_x_tc_gemm_2cta.so")   # same file eadgan_b200.build.build_experimental writes
 
 
 def build():
