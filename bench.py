@@ -200,7 +200,7 @@ def _main():
     parallel.attach(*step.optimizers())
 
     # global batch drawn once from the seeded host RNG, sharded contiguously (rank r: rows r*B..)
-    from oracle.torch_oracle import synth_celeba_images  # synthetic-input generator only (not on the timed path)
+    from eadgan_b200.synthetic import celeba_images as synth_celeba_images   # the oracle is only used by cpu_baseline
     R = 2  # ring of host batches
     host = []
     for i in range(R):

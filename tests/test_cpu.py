@@ -453,3 +453,14 @@ def test_tc_operand_layout_algebra():
     TF.conv2d(xt, wref, stride=2, padding=1).backward(dyt)
     assert np.abs(T.wgrad(x, dy) - wref.grad.numpy()).max() < 1e-12
     assert np.abs(T.dgrad(dy, w) - TF.conv_transpose2d(dyt, wt, stride=2, padding=1).numpy()).max() < 1e-12
+
+
+def test_benchmark_input_generator_equals_the_oracles():
+    from eadgan_b200 import synthetic
+    from oracle import torch_oracle as O
+    for seed in (0, 1, 7):
+        assert torch.equal(synthetic.celeba_images(5, seed), O.synth_celeba_images(5, seed))
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    main_arm = src[src.index("def _main():"):]
+    # the product arm of the benchmark touches the oracle only inside cpu_reference() (the cpu_baseline leg)
+    assert "from oracle" not in main_arm and "import oracle" not in main_arm
