@@ -24,6 +24,14 @@ def _fused(*ts):
     return all(t.is_cuda and t.dtype == torch.float32 for t in ts)
 
 
+def _require_fused(who, *ts):
+    """the product entry points run the fused kernels only: no CPU / other-dtype fallback (the ``*_torch``
+    restatements are for algebra checks and fp64 referees in the tests)"""
+    if not _fused(*ts):
+        raise RuntimeError(f"eadgan_b200.affine.{who}: CUDA float32 tensors required (no CPU fallback); "
+                           f"use {who}_torch for a reference evaluation on other tensors")
+
+
 def _mat3(rows):
     """rows: 3x3 nested list of [B] tensors / python floats -> [B,3,3]."""
     ref = next(e for r in rows for e in r if torch.is_tensor(e))
@@ -57,9 +65,8 @@ def _rzt_parts(code5):
 
 def celeba_relative_code(real_code, trans_code):
     """affine_regularzier of celebA/utils_rpqxy.py:82-116 (fused kernel on CUDA tensors)."""
-    if _fused(real_code, trans_code):
-        return Fn.relative_code(real_code, trans_code, Fn.REL_CELEBA)
-    return celeba_relative_code_torch(real_code, trans_code)
+    _require_fused("celeba_relative_code", real_code, trans_code)
+    return Fn.relative_code(real_code, trans_code, Fn.REL_CELEBA)
 
 
 def celeba_relative_code_torch(real_code, trans_code):
@@ -120,9 +127,8 @@ def dsprites_matrix23(code4):
 
 def dsprites_relative_code(real_code, trans_code):
     """affine_regularzier of dSprites/utils_rp.py:117-147 (fused kernel on CUDA tensors)."""
-    if _fused(real_code, trans_code):
-        return Fn.relative_code(real_code, trans_code, Fn.REL_DSPRITES)
-    return dsprites_relative_code_torch(real_code, trans_code)
+    _require_fused("dsprites_relative_code", real_code, trans_code)
+    return Fn.relative_code(real_code, trans_code, Fn.REL_DSPRITES)
 
 
 def dsprites_relative_code_torch(real_code, trans_code):
@@ -144,12 +150,16 @@ def dsprites_relative_code_torch(real_code, trans_code):
 
 
 # ---- colored dSprites (colored_dSprites/utils_rp_color.py) -------------------------------------------------
-def colored_relative_code(real_code, trans_code):
+def colored_relative_code(real_code, trans_code, _affine=None):
     """affine_color_regularzier of colored_dSprites/utils_rp_color.py:99-139: entries 0..3 as in
     dsprites_relative_code; entries 4..6 are the ratio of the colour gains c * 0.5 + 1 mapped back to a code."""
-    aff = dsprites_relative_code(real_code[:, :4], trans_code[:, :4])
+    aff = (_affine or dsprites_relative_code)(real_code[:, :4], trans_code[:, :4])
     rel = (trans_code[:, 4:] * 0.5 + 1) / (real_code[:, 4:] * 0.5 + 1)
     return torch.cat((aff, (rel - 1) / 0.5), dim=1)
+
+
+def colored_relative_code_torch(real_code, trans_code):
+    return colored_relative_code(real_code, trans_code, _affine=dsprites_relative_code_torch)
 
 
 # ---- MNIST (MNIST/utils_rpqmnxy.py) ------------------------------------------------------------------------
@@ -172,9 +182,8 @@ def mnist_matrix23(code7):
 
 def mnist_relative_rows(real_code, trans_code):
     """top two rows of M(trans) @ inverse(M(real)) as [B, 6] (fused kernel on CUDA tensors)."""
-    if _fused(real_code, trans_code):
-        return Fn.relative_code(real_code, trans_code, Fn.REL_MNIST)
-    return mnist_relative_rows_torch(real_code, trans_code)
+    _require_fused("mnist_relative_rows", real_code, trans_code)
+    return Fn.relative_code(real_code, trans_code, Fn.REL_MNIST)
 
 
 def mnist_relative_rows_torch(real_code, trans_code):

@@ -131,10 +131,10 @@ def test_mnist_affine_glue_matches_oracle():
     c1, c2 = torch.rand(32, 7, generator=g) * 2 - 1, torch.rand(32, 7, generator=g) * 2 - 1
     assert (affine.mnist_matrix23(c1) - O.mnist_get_matrix(c1)[:, 0:2]).abs().max() <= 1e-6
     rel = O.mnist_get_matrix(c2) @ torch.inverse(O.mnist_get_matrix(c1))
-    assert (affine.mnist_relative_rows(c1, c2) - torch.cat((rel[:, 0], rel[:, 1]), dim=1)).abs().max() <= 1e-5
+    assert (affine.mnist_relative_rows_torch(c1, c2) - torch.cat((rel[:, 0], rel[:, 1]), dim=1)).abs().max() <= 1e-5
     A = O.MnistAffineApproximator()
     want = O.mnist_affine_regularizer(c1, c2, A)
-    got = affine.mnist_code_from_params(A(affine.mnist_relative_rows(c1, c2)))
+    got = affine.mnist_code_from_params(A(affine.mnist_relative_rows_torch(c1, c2)))
     assert (got - want).abs().max() <= 1e-4
 
 
@@ -168,7 +168,7 @@ def test_colored_affine_glue_matches_oracle():
     from oracle import torch_oracle as O
     g = torch.Generator().manual_seed(5)
     c1, c2 = torch.rand(32, 7, generator=g) * 2 - 1, torch.rand(32, 7, generator=g) * 2 - 1
-    assert (affine.colored_relative_code(c1, c2) - O.colored_affine_color_regularizer(c1, c2)).abs().max() <= 1e-4
+    assert (affine.colored_relative_code_torch(c1, c2) - O.colored_affine_color_regularizer(c1, c2)).abs().max() <= 1e-4
 
 
 @pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference checkout not present (GPU box)")
@@ -211,7 +211,7 @@ def test_reference_affine_glue_matches():
     finally:
         torch.Tensor.cuda = saved
     for impl_m, impl_r in ((O.celeba_get_matrix, O.celeba_affine_regularizer),
-                           (affine.celeba_matrix, affine.celeba_relative_code)):
+                           (affine.celeba_matrix, affine.celeba_relative_code_torch)):
         assert (impl_m(c1[:, :5]) - m_ref).abs().max() <= 1e-6
         assert (impl_r(c1, c2) - r_ref).abs().max() <= 1e-4
 
@@ -246,7 +246,7 @@ def test_reference_dsprites_affine_glue_matches():
     assert (torch.inverse(O.dsprites_align_matrix(c3)) - al_ref).abs().max() <= 1e-6
     assert (affine.dsprites_align_inverse(c3) - al_ref[:, 0:2]).abs().max() <= 1e-6
     assert (O.dsprites_affine_regularizer(c1, c2) - r_ref).abs().max() <= 1e-5
-    assert (affine.dsprites_relative_code(c1, c2) - r_ref).abs().max() <= 1e-4
+    assert (affine.dsprites_relative_code_torch(c1, c2) - r_ref).abs().max() <= 1e-4
 
 
 def test_product_modules_mirror_reference_layout():
@@ -464,3 +464,12 @@ def test_benchmark_input_generator_equals_the_oracles():
     main_arm = src[src.index("def _main():"):]
     # the product arm of the benchmark touches the oracle only inside cpu_reference() (the cpu_baseline leg)
     assert "from oracle" not in main_arm and "import oracle" not in main_arm
+
+
+def test_affine_product_entry_points_have_no_cpu_fallback():
+    from eadgan_b200 import affine
+    c = torch.zeros(4, 7)
+    for fn in (affine.celeba_relative_code, affine.dsprites_relative_code, affine.mnist_relative_rows,
+               affine.colored_relative_code):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(c, c)
