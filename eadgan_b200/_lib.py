@@ -104,6 +104,7 @@ _PROTOS = {
     "eadgan_relcode_dims": [_I, _P, _P],
     "eadgan_relcode_fwd": [_I, _P, C.c_longlong, _P, C.c_longlong, _I, _P, _P, _P],
     "eadgan_relcode_bwd": [_I, _P, _P, _I, _P, _P, _P],
+    "eadgan_philox": [_I, C.c_ulonglong, _P, C.c_longlong, _I, C.c_longlong, C.c_longlong, C.c_longlong, _F, _F, _I, _P, _P],
 }
 _SPECIAL = {
     "eadgan_last_error": ([], C.c_char_p),

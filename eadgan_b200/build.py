@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = ["simt_conv.cu", "bn.cu", "elementwise.cu", "spectral_norm.cu", "loss_adam.cu", "tc_conv.cu", "glue.cu"]
+SRC = ["simt_conv.cu", "bn.cu", "elementwise.cu", "spectral_norm.cu", "loss_adam.cu", "tc_conv.cu", "glue.cu", "sample.cu"]
 
 
 def build(force=False, verbose=False):

@@ -38,6 +38,13 @@ def precision():
     return os.environ.get("EADGAN_PRECISION", "bf16")
 
 
+# tests only (tests/gates.py): when this is a list, every chain forward appends (sequential, [gate masks]) to it,
+# one bool NCHW mask per ReLU / LeakyReLU stage: mask = saved output > 0, which is exactly the gate the fused
+# backward kernels read.  A parity test replays these gates in the oracle so that both runs differentiate the
+# same piecewise-linear function (a single flipped gate moves every upstream gradient).
+gate_log = None
+
+
 def _pow2(v):
     return v > 0 and (v & (v - 1)) == 0
 
@@ -138,7 +145,17 @@ def prefetch_spectral_norm(seq, count=1):
             ev = torch.cuda.Event()
             ev.record(side)
             for conv, entry in zip(convs, done):
-                conv.__dict__.setdefault("_eadgan_sn_queue", []).append((entry, ev))
+                tag = getattr(getattr(conv, "weight_orig", None), "_eadgan_stepped", 0)
+                conv.__dict__.setdefault("_eadgan_sn_queue", []).append((entry, ev, tag))
+
+
+def set_trainable(module, flag):
+    """Step drivers freeze the networks the current phase's optimiser does not own (celebA/EAD-GAN_celebA.py:334-345:
+    phase G back-propagates THROUGH D, and the reference also computes D's weight gradients there, which
+    ``optimizer_D.zero_grad()`` (:353) discards unread).  With the parameters frozen autograd asks the chain for
+    input gradients only, so those dead weight-gradient GEMMs are never launched."""
+    for p in module.parameters():
+        p.requires_grad_(flag)
 
 
 def clear_prefetch(seq):
@@ -160,7 +177,11 @@ def try_run(seq, x):
         queue = st.conv.__dict__.get("_eadgan_sn_queue")
         if queue:
             # this forward's power iteration was issued ahead of time (prefetch_spectral_norm): adopt its results
-            (w_pre, sn_pre), ev = queue.pop(0)
+            (w_pre, sn_pre), ev, tag = queue.pop(0)
+            if tag != getattr(getattr(st.conv, "weight_orig", None), "_eadgan_stepped", 0):
+                raise RuntimeError("eadgan_b200.chain: a prefetched spectral-norm result is older than the layer's "
+                                   "weights (an optimiser stepped them after prefetch_spectral_norm); the step driver "
+                                   "must prefetch only forwards that run before the owning optimiser steps")
             cur = torch.cuda.current_stream()
             cur.wait_event(ev)
             for t in (w_pre,) + (tuple(sn_pre[1:3]) if sn_pre is not None else ()):
@@ -196,6 +217,8 @@ def try_run(seq, x):
         if st.bn is not None:
             st.bn.num_batches_tracked.add_(1)
             params += [st.bn.weight, st.bn.bias]
+    if gate_log is not None:
+        gate_log.append((seq, []))
     return _ChainFn.apply(x, stages, srcs, *params)
 
 
@@ -327,7 +350,7 @@ class _ChainFn(torch.autograd.Function):
             stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if st.bn is not None else None
             wc = w.contiguous()
             impl = _impl(st, d, last)
-            rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl}
+            rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl, "pi": pi - (4 if st.bn is not None else 2)}
             src = srcs[si]
             lazy = [src is not None and len(src) > 2 and bool(src[2])]
 
@@ -419,6 +442,8 @@ class _ChainFn(torch.autograd.Function):
                            sum_x=sum_x)
                 out = y
             rec["y"] = out
+            if gate_log is not None and st.act[0] in (L.ACT_RELU, L.ACT_LRELU):
+                gate_log[-1][1].append(out.view() > 0)
             saved.append(rec)
             cur = out
         # the returned tensor is saved through autograd (no ctx <-> output reference cycle)
@@ -443,6 +468,11 @@ class _ChainFn(torch.autograd.Function):
             cout = d.k if st.kind == "conv" else d.c
             n, _, oh, ow = sv["y"].nchw
             dgamma = dbeta = None
+            # which parameter gradients autograd actually wants (inputs: x, stages, srcs, then w, b[, gamma, beta] per
+            # stage).  A step driver freezes the networks a phase's optimiser does not own (phase G: D), so their
+            # weight-gradient GEMMs, bias sums and spectral-norm backward are never launched
+            need_dw = ctx.needs_input_grad[3 + sv["pi"]]
+            need_db = sv["has_b"] and ctx.needs_input_grad[3 + sv["pi"] + 1]
             # ---- 1. gradient w.r.t. the conv output (pre-BN / pre-activation) ----------------
             if st.bn is not None:
                 sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
@@ -470,7 +500,7 @@ class _ChainFn(torch.autograd.Function):
                 dz = _Buf(Fn.act_bwd(g.t, sv["y"].t, st.act[0], st.act[1]), "ext")
             else:
                 dz = g
-            if not sv["has_b"]:
+            if not need_db:
                 db = None
             elif st.bn is not None:
                 db = db_bn
@@ -490,14 +520,18 @@ class _ChainFn(torch.autograd.Function):
             # its activation backward is fused (or absent): let the producing epilogue also sum it per channel
             # (= that stage's bias gradient), instead of a separate pass over dx
             want_sums = (need_dx and prev is not None and prev.bn is None and saved[si - 1]["has_b"]
+                         and ctx.needs_input_grad[3 + saved[si - 1]["pi"] + 1]
                          and (fuse or prev.act[0] == ACT_NONE) and in_shape[1] <= 1024)
             sums_buf = torch.zeros(in_shape[1], device=dev, dtype=torch.float64) if want_sums else None
             sums_used = False
             # ---- 2./3. weight gradient and input gradient -----------------------------------------
             if impl == "thin":
+                dw = None
                 if st.kind == "conv":      # big map = stage input (image), small map = dz
                     r = sv["R"]
-                    if _thin_ok(d, "wgrad"):
+                    if not need_dw:
+                        pass
+                    elif _thin_ok(d, "wgrad"):
                         dw = tc.thin_wgrad(r, dz.padded(), d.c)
                     else:
                         dw = torch.empty_like(sv["w"])
@@ -506,8 +540,10 @@ class _ChainFn(torch.autograd.Function):
                         wpk, sg = sv["packed_thin"]("dgrad")
                         dx = _Buf(tc.thin_dgrad(dz.padded(), wpk, None, d.c, sigma=sg), "ext")
                 else:                      # big map = dz (image gradient), small map = stage input
-                    r = tc.thin_expand(dz.view())
-                    if _thin_ok(d, "wgrad"):
+                    r = tc.thin_expand(dz.view()) if (need_dw or (need_dx and si > 0)) else None
+                    if not need_dw:
+                        pass
+                    elif _thin_ok(d, "wgrad"):
                         dw = tc.thin_wgrad(r, sv["inp"].t, d.c)
                     else:
                         dw = torch.empty_like(sv["w"])
@@ -519,10 +555,10 @@ class _ChainFn(torch.autograd.Function):
                                                 sigma=sg), "pad")
                         sums_used = want_sums
             elif impl == "dense_T":
-                dw = tc.dense_wgrad(sv["a"], dz.padded(), d.k)
+                dw = tc.dense_wgrad(sv["a"], dz.padded(), d.k) if need_dw else None
             elif impl == "dense_C":
                 a = tc.pad_rows(dz.t.reshape(d.n, d.k), 64)
-                dw = tc.dense_wgrad(a, sv["inp"].t, d.k)
+                dw = tc.dense_wgrad(a, sv["inp"].t, d.k) if need_dw else None
                 if need_dx and (si > 0) and (not fuse or sv["inp"].fmt == "pad"):
                     dx = _Buf(tc.dense_scatter(a, tc.dense_pack(sv["wvals"](), 64, False), None, d.c,
                                                mask=sv["inp"].t if fuse else None, mask_act=mask_act,
@@ -531,7 +567,9 @@ class _ChainFn(torch.autograd.Function):
             else:
                 ca = _calloc(d) if impl == "tc" else d.c
                 x_big, dy_small = (sv["inp"], dz) if st.kind == "conv" else (dz, sv["inp"])
-                if impl == "tc" and _tc_ok(d, "wgrad"):
+                if not need_dw:
+                    dw = None
+                elif impl == "tc" and _tc_ok(d, "wgrad"):
                     xb = x_big.t if x_big.fmt == "pad" else tc.to_padded(x_big.t, ca)
                     if st.kind == "convT" and ca != d.c:
                         dz = _Buf(xb, "pad")  # reuse the channel-padded copy for the input gradient below

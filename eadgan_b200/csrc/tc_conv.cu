@@ -27,7 +27,9 @@
 // tiles with 128-byte swizzle, full/empty mbarriers, tcgen05.commit releases slots.
 #include <cuda.h>
 
+#include <atomic>
 #include <mutex>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -72,53 +74,128 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
+// TMA tiled loads.  `bar` is a shared::cluster ADDRESS (uint32): the CTA's own barrier for cta_group::1 kernels,
+// the LEADER CTA's barrier (mapa to rank 0) for cta_group::2 kernels, whose loads land in the issuing CTA's shared
+// memory but signal their bytes on the pair leader's full barrier (CUTLASS SM100_TMA_2SM_LOAD_*).
+template <int CG>
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  if constexpr (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4}], [%2];" ::"r"(smem_u32(dst)), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+template <int CG>
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
-      "[%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+        "[%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+template <int CG>
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
-      "%7}], [%2];" ::"r"(smem_u32(dst)),
-      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, "
+        "%7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, "
+        "%4, %5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+// ---- thread-block cluster / CTA pair (cta_group::2) helpers ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on a barrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+template <int CG = 1>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-               "r"(ncols)
-               : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if constexpr (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {   // issued by the same warp of BOTH CTAs of the pair, same destination offset
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG = 1>
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+  else
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate
+// cta_group::2: issued by the pair LEADER only; the instruction spans both SMs (M = 256: rows 0..127 from the
+// leader's A tile, 128..255 from the peer's, at the same shared-memory offsets; each CTA holds half of the B rows)
+template <int CG = 1>
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
+  if constexpr (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
+// arrive on `bar` once every MMA issued so far has completed; cta_group::2: on the barrier at the same
+// shared-memory offset in BOTH CTAs of the pair (multicast, mask 0b11)
+template <int CG = 1>
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
+  if constexpr (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+                 : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
@@ -191,11 +268,16 @@ constexpr int BLOCK_K = 64;
 constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;  // 16 KB
 constexpr int STAT_MAX_CH = 1024;               // per-CTA running statistics cover up to this many channels
 
-template <int BLOCK_N, int MT>   // MT = number of 128-row M tiles per CTA tile (1 or 2): MT = 2 halves the B re-reads
+// MT = number of 128-row M tiles per CTA tile (1 or 2): MT = 2 halves the B re-reads.
+// CG = tcgen05 cta_group: 1 = one CTA computes a (MT x 128) x BLOCK_N tile; 2 = a CTA PAIR (cluster of two SMs of one
+// TPC) computes (2 x MT x 128) x BLOCK_N with one MMA stream issued by the pair leader: each CTA stages its own A rows
+// and only HALF of the B rows, so the shared-memory traffic per MAC (TMA writes + MMA operand reads) drops by a third
+// at BLOCK_N = 256 (125 instead of 188 B/clk/SM at full tensor rate), and the ring is 6 stages of 32 KB instead of 4 of 48.
+template <int BLOCK_N, int MT, int CG>
 struct Cfg {
-  static constexpr int B_BYTES = BLOCK_N * BLOCK_K * 2;
+  static_assert(CG == 1 || CG == 2, "cta_group");
+  static constexpr int B_BYTES = (BLOCK_N / CG) * BLOCK_K * 2;  // this CTA's share of the B tile
   static constexpr int STAGE_BYTES = MT * A_BYTES + B_BYTES;
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES < 8 ? (192 * 1024) / STAGE_BYTES : 8;
   static constexpr int ACC_COLS = BLOCK_N < 32 ? 32 : BLOCK_N;  // TMEM columns of ONE 128-row accumulator
   static constexpr int BUF_COLS = MT * ACC_COLS;                // one accumulator buffer (MT sub-tiles)
   static constexpr int TMEM_COLS = 2 * BUF_COLS;                // two buffers: epilogue(i) overlaps mainloop(i+1)
@@ -204,8 +286,11 @@ struct Cfg {
   static constexpr int STAT_PART_BYTES = 4 * BLOCK_N * 2 * 4;   // float [4 warps][BLOCK_N][2]
   static constexpr int STAT_ACC_BYTES = STAT_MAX_CH * 2 * 8;    // double [channels][2]
   static constexpr int BIAS_BYTES = STAT_MAX_CH * 4;            // float [channels]: the bias vector, staged once
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + BAR_BYTES + STAT_PART_BYTES + STAT_ACC_BYTES +
-                              BIAS_BYTES;
+  static constexpr int FIXED_BYTES = 1024 /*align*/ + BAR_BYTES + STAT_PART_BYTES + STAT_ACC_BYTES + BIAS_BYTES;
+  static constexpr int RING_BUDGET = 227 * 1024 - FIXED_BYTES;
+  static constexpr int STAGES = RING_BUDGET / STAGE_BYTES < 8 ? RING_BUDGET / STAGE_BYTES : 8;
+  static_assert(2 * STAGES + 4 <= BAR_BYTES / 8 - 1, "barrier block too small");
+  static constexpr int SMEM = STAGES * STAGE_BYTES + FIXED_BYTES;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -242,11 +327,11 @@ struct RowInfo {
   int n0, bias_base;
   int64_t out_off, ch_stride, mask_off;
 };
-template <int BLOCK_N, int MT>
-__device__ __forceinline__ RowInfo row_info(const TcParams& P, int tile, int h, int row) {
+template <int BLOCK_N, int MT, int CG>
+__device__ __forceinline__ RowInfo row_info(const TcParams& P, int tile, int h, int row, int rank) {
   RowInfo ri;
   const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
-  const int parity = r % P.parities, m_tile = (r / P.parities) * MT + h;
+  const int parity = r % P.parities, m_tile = ((r / P.parities) * CG + rank) * MT + h;
   const int py = parity >> 1, px = parity & 1;
   const int n0 = n_tile * BLOCK_N;
   ri.n0 = n0; ri.bias_base = n0; ri.out_off = 0; ri.ch_stride = 1; ri.mask_off = 0;
@@ -290,11 +375,11 @@ __device__ __forceinline__ RowInfo row_info(const TcParams& P, int tile, int h, 
 // fprop / dgrad / gemm kernel.  PERSISTENT: grid <= number of SMs, CTA c runs tiles c, c+grid, ...
 // (n-tile fastest so concurrently running CTAs share the streamed A operand through L2).
 // ------------------------------------------------------------------------------------
-template <int BLOCK_N, int MT>
+template <int BLOCK_N, int MT, int CG>
 __global__ void __launch_bounds__(320, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                const TcParams P) {
-  using C = Cfg<BLOCK_N, MT>;
+  using C = Cfg<BLOCK_N, MT, CG>;
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSETTING the shared array (not by integer round trip): the compiler keeps the shared address
   // space, so every access below is LDS/STS instead of a generic LD/ST through the L1TEX path
@@ -312,6 +397,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.parities * P.m_tiles * P.n_tiles;
+  // cta_group::2: the two CTAs of a pair walk the SAME tile list (first = pair index, step = number of pairs);
+  // rank 0 is the leader (issues the MMAs, owns the full / accumulator-empty barriers both CTAs signal)
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int first_tile = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -319,12 +409,17 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   if (warp == 1) {
     if (lane == 0) {
+      // full: ONE arrival -- the leader's arrive.expect_tx of the bytes of BOTH CTAs; the peer only issues its loads,
+      // whose bytes complete on the leader's barrier (a peer load can land before the leader's expect_tx of the same
+      // phase: the transaction count is then transiently negative, which mbarriers allow; it cannot land in an
+      // earlier phase, because the slot is only released once the MMAs that consumed that phase have completed)
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+      // accumulator empty: the 8 epilogue warps of every CTA of the group
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8 * CG); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    tmem_alloc<CG>(tmem_ptr, C::TMEM_COLS);
   }
   if (warp >= 2) {
     if (P.want_stats) {
@@ -337,25 +432,33 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();   // the peer's barriers exist before anybody signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one per CTA: its own A rows and its share of the B rows) =====
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
         const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
         // parity next-fastest: the 4 output parities of an M tile read the SAME input tile (shifted taps), so they
         // run back to back / side by side and share it through L2 instead of re-streaming it from HBM 4 times
-        const int parity = r % P.parities, m_grp = r / P.parities;   // m_grp: group of MT consecutive 128-row tiles
+        const int parity = r % P.parities;
+        const int m_grp = (r / P.parities) * CG + rank;   // this CTA's group of MT consecutive 128-row tiles
         const int py = parity >> 1, px = parity & 1;
-        const int n0 = n_tile * BLOCK_N;
+        const int n0 = n_tile * BLOCK_N + rank * (BLOCK_N / CG);      // first B row this CTA stages
         for (int kb = 0; kb < P.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + MT * A_BYTES;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint32_t fb = smem_u32(&full_bar[stage]);
+          if constexpr (CG == 2) {
+            fb = mapa(fb, 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          } else {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          }
           // dense gather: the K range (16 taps x channels) is split over the "parity" index (split-K)
           const int kbg = P.mode == MODE_DENSE_GATHER ? parity * P.nkb + kb : kb;
           const int qi = kbg % P.qblocks, t = kbg / P.qblocks;
@@ -364,40 +467,40 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             const int m_tile = m_grp * MT + h;
             uint8_t* sah = sa + h * A_BYTES;
             if (P.mode == MODE_GEMM) {
-              tma_load_2d(sah, &map_a, &full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+              tma_load_2d<CG>(sah, &map_a, fb, kb * BLOCK_K, m_tile * BLOCK_M);
             } else if (P.mode == MODE_DENSE_GATHER) {
               // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]  (t = tap)
-              tma_load_4d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + (t & 3), 1 + (t >> 2), m_tile * BLOCK_M);
+              tma_load_4d<CG>(sah, &map_a, fb, qi * BLOCK_K, 1 + (t & 3), 1 + (t >> 2), m_tile * BLOCK_M);
             } else {
               const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
               if (P.mode == MODE_FPROP && P.thin) {
                 // R[n][oy][X][ky][4]: the 4x4x4 patch of output (oy, ox) is the 64 contiguous elements at X = 2 ox
-                tma_load_4d(sah, &map_a, &full_bar[stage], 0, 0, y0, b0);
+                tma_load_4d<CG>(sah, &map_a, fb, 0, 0, y0, b0);
               } else if (P.mode == MODE_FPROP) {
                 const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-                tma_load_5d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, bt, dy, y0 + at, b0);
+                tma_load_5d<CG>(sah, &map_a, fb, qi * BLOCK_K, bt, dy, y0 + at, b0);
               } else {  // t = ty*2+tx
                 const int ty = t >> 1, tx = t & 1;
                 const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
                 const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
-                tma_load_4d(sah, &map_a, &full_bar[stage], qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
+                tma_load_4d<CG>(sah, &map_a, fb, qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
               }
             }
           }
           // dgrad: tap t's weights start at column t * K_ch (= kb * 64 whenever K_ch is a multiple of 64; for
           // K_ch = 32 the box also covers 32 columns of the next tap, multiplied by the zero-filled half of A)
-          tma_load_2d(sb, &map_b, &full_bar[stage], P.mode == MODE_DGRAD ? t * P.K_ch + qi * BLOCK_K : kbg * BLOCK_K,
+          tma_load_2d<CG>(sb, &map_b, fb, P.mode == MODE_DGRAD ? t * P.K_ch + qi * BLOCK_K : kbg * BLOCK_K,
                       (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, 0, 0);
+    // ===== MMA issuer (cta_group::2: the pair leader only; its instructions drive both SMs) =====
+    constexpr uint32_t idesc = make_idesc(BLOCK_M * CG, BLOCK_N, 0, 0);
     int stage = 0; uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles && rank == 0; tile += tile_step, ++it) {
       const int buf = it & 1;
       mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
       tc_fence_after();
@@ -414,11 +517,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
             for (int h = 0; h < MT; ++h) {
               const uint64_t da = make_desc(sa + h * A_BYTES + k * 32, 16, 1024);
-              umma_bf16(d_tmem + (uint32_t)(h * C::ACC_COLS), da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              umma_bf16<CG>(d_tmem + (uint32_t)(h * C::ACC_COLS), da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (kb == P.nkb - 1) umma_commit(&tmem_full_bar[buf]);
+          umma_commit<CG>(&empty_bar[stage]);                         // frees the slot in both CTAs
+          if (kb == P.nkb - 1) umma_commit<CG>(&tmem_full_bar[buf]);  // wakes the epilogue warps of both CTAs
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -433,16 +536,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int et = threadIdx.x - 64;      // 0..255
     constexpr int NCHUNK = BLOCK_N / 32;
     const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
+    // the accumulator-empty barriers live in the pair leader (the MMA issuer waits on them)
+    uint32_t te_bar[2] = {smem_u32(&tmem_empty_bar[0]), smem_u32(&tmem_empty_bar[1])};
+    if constexpr (CG == 2) { te_bar[0] = mapa(te_bar[0], 0); te_bar[1] = mapa(te_bar[1], 0); }
+    auto te_arrive = [&](int b) {
+      if constexpr (CG == 2) mbar_arrive_cluster(te_bar[b]);
+      else mbar_arrive(&tmem_empty_bar[b]);
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++it) {
       if (P.mask_mode) {
         // pull the NEXT tile's mask rows into L2 now: by the time its accumulator is ready the loads below
         // are L2 hits instead of DRAM round trips (the epilogue is latency-bound otherwise)
-        const int nt = tile + gridDim.x;
+        const int nt = tile + tile_step;
         if (nt < total_tiles) {
 #pragma unroll
           for (int h = 0; h < MT; ++h) {
-            const RowInfo ri = row_info<BLOCK_N, MT>(P, nt, h, row);
+            const RowInfo ri = row_info<BLOCK_N, MT, CG>(P, nt, h, row, rank);
             if (ri.valid) {
               for (int l = half; l < (BLOCK_N >= 64 ? BLOCK_N / 64 : 1); l += 2)
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mask + ri.mask_off + l * 64));
@@ -454,11 +564,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       if (half >= NCHUNK) {  // BLOCK_N = 32: the second warp of each quadrant has no columns
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        if (lane == 0) te_arrive(buf);
       }
 #pragma unroll 1
       for (int h = 0; h < MT; ++h) {
-        const RowInfo ri = row_info<BLOCK_N, MT>(P, tile, h, row);
+        const RowInfo ri = row_info<BLOCK_N, MT, CG>(P, tile, h, row, rank);
         const bool valid = ri.valid, f32_out = ri.f32_out;
         const int n0 = ri.n0, bias_base = ri.bias_base;
         const int64_t ch_stride = ri.ch_stride;
@@ -481,7 +591,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             // all of this warp's columns are in registers: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            if (lane == 0) te_arrive(buf);
           }
           if (P.sigma) {
 #pragma unroll
@@ -583,7 +693,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           // Each warp keeps fp32 running column sums of ITS rows / chunks in stat_part (no sharing, no barrier).
           // They are folded into the CTA's fp64 per-channel totals only when the next tile of this CTA covers a
           // different channel block (or there is no next tile): thread et owns channel bias_base + et [+ 256 ...]
-          const int nt = tile + gridDim.x;
+          const int nt = tile + tile_step;
           const bool fold = nt >= total_tiles || (nt % P.n_tiles) != (tile % P.n_tiles) ||
                             (P.dense_C > 0);
           if (fold) {
@@ -620,7 +730,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+  if constexpr (CG == 2) cluster_sync();   // the leader's MMAs read the peer's shared memory: nobody leaves early
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
 }
 
 // ------------------------------------------------------------------------------------
@@ -641,23 +752,27 @@ struct WgParams {
   int kk_tiles, ko_tiles, splits;   // persistent item space (filled by launch_wgrad from the logical grid)
 };
 
-template <int BLOCK_N>  // BLOCK_N columns of kk per tile (multiple of 64)
+// BLOCK_N columns of kk per tile (multiple of 64).  CG = 2: a CTA pair computes 256 ko rows x BLOCK_N columns; each
+// CTA stages the dy box of ITS 128 ko rows and HALF of the patch columns (32 KB per stage instead of 48).
+template <int BLOCK_N, int CG>
 struct WgCfg {
   static constexpr int A_B = 2 * 64 * 128;               // two 64-channel boxes x 64 pixels
-  static constexpr int B_B = (BLOCK_N / 64) * 64 * 128;
+  static constexpr int NB = BLOCK_N / 64 / CG;           // 64-column patch boxes this CTA stages
+  static constexpr int B_B = NB * 64 * 128;
   static constexpr int STAGE_BYTES = A_B + B_B;
-  static constexpr int STAGES = BLOCK_N >= 256 ? 4 : 6;
+  static constexpr int STAGES = CG == 2 ? 6 : (BLOCK_N >= 256 ? 4 : 6);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256;
+  static_assert(SMEM <= 227 * 1024, "wgrad ring exceeds shared memory");
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, int CG>
 __global__ void __launch_bounds__(192, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constant__ CUtensorMap map_x,
                 const WgParams P) {
   // PERSISTENT: work items are (split, ko tile, kk tile) triples, kk fastest; CTA c runs items c, c + grid, ...
   // Two TMEM accumulators: the epilogue of item i (128 x BLOCK_N fp32 partial -> global) overlaps the
   // mainloop of item i + 1, and barrier / TMEM / tensor-map set-up is paid once per CTA instead of per item.
-  using C = WgCfg<BLOCK_N>;
+  using C = WgCfg<BLOCK_N, CG>;
   extern __shared__ uint8_t smem_raw[];
   // align by OFFSETTING the shared array (not by integer round trip): the compiler keeps the shared address
   // space, so every access below is LDS/STS instead of a generic LD/ST through the L1TEX path
@@ -671,59 +786,72 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles = P.kk_tiles * P.ko_tiles;
   const int total_items = tiles * P.splits;
+  // cta_group::2: both CTAs of a pair walk the same item list; rank 0 leads (see tc_conv_kernel)
+  const int rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int first_item = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_dy); tma_prefetch_desc(&map_x); }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 4 * CG); }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, 2 * BLOCK_N);
+    tmem_alloc<CG>(tmem_ptr, 2 * BLOCK_N);
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 0) {
     if (elect_one()) {
       int stage = 0; uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      for (int item = first_item; item < total_items; item += item_step) {
         const int kk_tile = item % P.kk_tiles, ko_tile = (item / P.kk_tiles) % P.ko_tiles, split = item / tiles;
+        const int ko0 = (ko_tile * CG + rank) * 128;                 // this CTA's 128 dy channels
+        const int nb0 = (kk_tile * CG + rank) * C::NB;               // ... and its first 64-column patch block
         const int step0 = split * P.steps_per_split;
         const int step1 = min(P.steps_total, step0 + P.steps_per_split);
         for (int st = step0; st < step1; ++st) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_B;
-          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint32_t fb = smem_u32(&full_bar[stage]);
+          if constexpr (CG == 2) {
+            fb = mapa(fb, 0);
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+          } else {
+            mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          }
           if (P.dense) {
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              tma_load_2d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, st * 64);
+              tma_load_2d<CG>(sa + h * 8192, &map_dy, fb, ko0 + h * 64, st * 64);
 #pragma unroll
-            for (int i = 0; i < BLOCK_N / 64; ++i) {
-              const int nb = kk_tile * (BLOCK_N / 64) + i;
+            for (int i = 0; i < C::NB; ++i) {
+              const int nb = nb0 + i;
               const int qi = nb % P.qblocks, tap = nb / P.qblocks;  // tap = ky*4+kx
-              tma_load_4d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
+              tma_load_4d<CG>(sb + i * 8192, &map_x, fb, qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
             }
           } else {
             const int b0 = (st / P.tiles_y) * P.Tb;
             const int y0 = (st % P.tiles_y) * P.Th;
 #pragma unroll
             for (int h = 0; h < 2; ++h)
-              tma_load_4d(sa + h * 8192, &map_dy, &full_bar[stage], ko_tile * 128 + h * 64, 1, y0 + 1, b0);
+              tma_load_4d<CG>(sa + h * 8192, &map_dy, fb, ko0 + h * 64, 1, y0 + 1, b0);
             if (P.thin) {
-              tma_load_4d(sb, &map_x, &full_bar[stage], 0, 0, y0, b0);
+              tma_load_4d<CG>(sb, &map_x, fb, 0, 0, y0, b0);
             } else {
 #pragma unroll
-              for (int i = 0; i < BLOCK_N / 64; ++i) {
-                const int nb = kk_tile * (BLOCK_N / 64) + i;  // 64-wide column block index
+              for (int i = 0; i < C::NB; ++i) {
+                const int nb = nb0 + i;  // 64-wide column block index
                 const int qi = nb % P.qblocks, t = nb / P.qblocks;
                 const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-                tma_load_5d(sb + i * 8192, &map_x, &full_bar[stage], qi * 64, bt, dy, y0 + at, b0);
+                tma_load_5d<CG>(sb + i * 8192, &map_x, fb, qi * 64, bt, dy, y0 + at, b0);
               }
             }
           }
@@ -732,10 +860,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = make_idesc(128, BLOCK_N, 1, 1);  // both operands MN-major
+    constexpr uint32_t idesc = make_idesc(128 * CG, BLOCK_N, 1, 1);  // both operands MN-major
     int stage = 0; uint32_t phase = 0;
     int use = 0;   // accumulator uses so far (items with at least one step)
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (int item = first_item; item < total_items && rank == 0; item += item_step) {
       const int split = item / tiles;
       const int step0 = split * P.steps_per_split;
       const int nsteps = min(P.steps_total, step0 + P.steps_per_split) - step0;
@@ -754,10 +882,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           for (int k = 0; k < 4; ++k) {  // 16 pixel rows per MMA
             const uint64_t da = make_desc(sa + k * 2048, 8192, 1024);
             const uint64_t db = make_desc(sb + k * 2048, 8192, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16<CG>(d_tmem, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);
-          if (it == nsteps - 1) umma_commit(&tmem_full_bar[buf]);
+          umma_commit<CG>(&empty_bar[stage]);
+          if (it == nsteps - 1) umma_commit<CG>(&tmem_full_bar[buf]);
         }
         __syncwarp();
         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -766,12 +894,14 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
     }
   } else {
     const int quad = warp & 3;
+    uint32_t te_bar[2] = {smem_u32(&tmem_empty_bar[0]), smem_u32(&tmem_empty_bar[1])};
+    if constexpr (CG == 2) { te_bar[0] = mapa(te_bar[0], 0); te_bar[1] = mapa(te_bar[1], 0); }
     int use = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+    for (int item = first_item; item < total_items; item += item_step) {
       const int kk_tile = item % P.kk_tiles, ko_tile = (item / P.kk_tiles) % P.ko_tiles, split = item / tiles;
       const int step0 = split * P.steps_per_split;
       const int nsteps = min(P.steps_total, step0 + P.steps_per_split) - step0;
-      const int ko = ko_tile * 128 + quad * 32 + lane;
+      const int ko = (ko_tile * CG + rank) * 128 + quad * 32 + lane;
       const int buf = use & 1;
       if (nsteps > 0) {
         mbar_wait(&tmem_full_bar[buf], (use >> 1) & 1);
@@ -786,7 +916,10 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
           if (c0 + 32 >= BLOCK_N) {   // every column of this warp's rows is in registers: release the accumulator
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+            if (lane == 0) {
+              if constexpr (CG == 2) mbar_arrive_cluster(te_bar[buf]);
+              else mbar_arrive(&tmem_empty_bar[buf]);
+            }
           }
         } else {
 #pragma unroll
@@ -803,7 +936,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  if constexpr (CG == 2) cluster_sync();
+  if (warp == 1) tmem_dealloc<CG>(tmem_base, 2 * BLOCK_N);
 }
 
 // sum split partials and permute GEMM column order (a,b,dy,dx,c) -> dw[ko][c][ky][kx]
@@ -976,6 +1110,21 @@ int map_matrix(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, u
   return encode_map(m, base, 2, dims, st, box);
 }
 
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) applies PER DEVICE: remember which devices have been opted in
+// (bit d of an atomic mask; devices >= 64 simply set the attribute on every launch).  Safe from any thread
+// (backward runs on autograd's per-device worker threads).
+template <typename K>
+int opt_in_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
+  int dev = 0;
+  EG_CUDA(cudaGetDevice(&dev));
+  const uint64_t bit = dev < 64 ? (1ull << dev) : 0ull;
+  if (bit && (done.load(std::memory_order_acquire) & bit)) return 0;
+  EG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (bit) done.fetch_or(bit, std::memory_order_release);
+  return 0;
+}
+
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // tile of `pixels` positions of a p x q grid: Tw = q, Th rows, Tb images
@@ -989,44 +1138,78 @@ int pick_tile(int p, int q, int pixels, int* Tw, int* Th, int* Tb) {
   return 0;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, int CG>
 int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(tc_conv_kernel<BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN, MT>::SMEM));
-    attr_set = true;
-  }
-  // persistent grid: every CTA runs the same number of tiles (+-1), at most one CTA per SM
+  static std::atomic<uint64_t> opted{0};
+  if (int e = opt_in_smem(tc_conv_kernel<BN, MT, CG>, Cfg<BN, MT, CG>::SMEM, opted)) return e;
+  // persistent grid: every CTA (CTA pair) runs the same number of tiles (+-1), at most one CTA per SM
   const int total = P.parities * P.m_tiles * P.n_tiles;
-  const int sms = eg_sm_count();
-  const int waves = (total + sms - 1) / sms;
-  const int grid = (total + waves - 1) / waves;
-  tc_conv_kernel<BN, MT><<<grid, 320, Cfg<BN, MT>::SMEM, st>>>(ma, mb, P);
+  int units = eg_sm_count() / CG;
+  if (const char* e = getenv("EADGAN_TC_UNITS")) { if (atoi(e) > 0 && atoi(e) < units) units = atoi(e); }   // experiments
+  const int waves = (total + units - 1) / units;
+  const int grid = ((total + waves - 1) / waves) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(320); cfg.dynamicSmemBytes = Cfg<BN, MT, CG>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CG == 2 ? 1 : 0;
+  if (CG == 2 && getenv("EADGAN_TC_DEBUG")) {
+    int nc = -1;
+    cudaLaunchConfig_t q = cfg; q.gridDim = dim3(2 * eg_sm_count());
+    cudaError_t er = cudaOccupancyMaxActiveClusters(&nc, tc_conv_kernel<BN, MT, CG>, &q);
+    fprintf(stderr, "[eadgan] tc_conv<%d,%d,%d>: grid %d, total %d tiles, max active clusters %d (%s)\n", BN, MT, CG, grid,
+            total, nc, cudaGetErrorString(er));
+  }
+  EG_CUDA(cudaLaunchKernelEx(&cfg, tc_conv_kernel<BN, MT, CG>, ma, mb, P));
   EG_LAUNCH_CHECK("tc_conv_kernel");
   return 0;
 }
 
-int dispatch_conv(int bn, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& P, int m_tiles, int n_total,
-                  int parities, cudaStream_t st) {
+// tile configuration of one launch: BLOCK_N, M tiles per CTA, cta_group
+struct TileCfg { int bn, mt, cg; };
+
+int pick_bn_tiles(int nch, int m_tiles_x_par);
+
+// cg = 2 (CTA pairs, see Cfg) for the layers with enough tiles to keep every pair busy for several tiles; the small /
+// ragged launches (dSprites 32..64-channel layers, dense and thin GEMMs) stay on the single-CTA path.
+TileCfg pick_cfg(int nch, int m_tiles, int parities, bool allow_pair, int force_bn = 0) {
+  TileCfg t;
+  t.bn = force_bn ? force_bn : pick_bn_tiles(nch, m_tiles * parities);
+  if (t.bn <= 0) return t;
+  const int sms = eg_sm_count();
+  const int64_t tiles = (int64_t)m_tiles * parities * (nch / t.bn);
+  t.cg = (allow_pair && t.bn >= 128 && m_tiles >= 2 && tiles >= 2 * sms) ? 2 : 1;
+  if (const char* e = getenv("EADGAN_TC_CG")) { if (allow_pair && t.bn >= 128 && (atoi(e) == 1 || atoi(e) == 2)) t.cg = atoi(e); }
   // two 128-row tiles per CTA tile (sharing every B load) when BLOCK_N <= 128 and there is enough work
-  int mt = (bn <= 128 && (int64_t)m_tiles * parities * (n_total / bn) >= 4 * eg_sm_count()) ? 2 : 1;
-  if (const char* e = getenv("EADGAN_TC_MT")) { if (bn <= 128 && atoi(e) >= 1 && atoi(e) <= 2) mt = atoi(e); }
-  P.m_tiles = (m_tiles + mt - 1) / mt; P.n_tiles = n_total / bn; P.parities = parities;
+  t.mt = (t.bn <= 128 && tiles >= 4 * sms * t.cg) ? 2 : 1;
+  if (const char* e = getenv("EADGAN_TC_MT")) { if (t.bn <= 128 && atoi(e) >= 1 && atoi(e) <= 2) t.mt = atoi(e); }
+  return t;
+}
+
+int dispatch_conv(const TileCfg& t, const CUtensorMap& ma, const CUtensorMap& mb, TcParams& P, int m_tiles, int n_total,
+                  int parities, cudaStream_t st) {
+  const int bn = t.bn, mt = t.mt, per = t.mt * t.cg;
+  P.m_tiles = (m_tiles + per - 1) / per; P.n_tiles = n_total / bn; P.parities = parities;
   P.bias_len = P.bias ? (P.dense_C > 0 ? P.dense_C : P.n_store) : 0;
   EG_REQUIRE(P.bias_len <= STAT_MAX_CH, EADGAN_ERR_UNSUPPORTED, "tc conv: fused bias supports at most %d channels (got %d)",
              STAT_MAX_CH, P.bias_len);
   EG_REQUIRE(!P.want_stats || (P.stat_channels > 0 && P.stat_channels <= STAT_MAX_CH), EADGAN_ERR_UNSUPPORTED,
              "tc conv: fused statistics support at most %d channels (got %d)", STAT_MAX_CH, P.stat_channels);
-  switch (bn * 10 + mt) {
-    case 321: return launch_conv<32, 1>(ma, mb, P, st);
-    case 322: return launch_conv<32, 2>(ma, mb, P, st);
-    case 641: return launch_conv<64, 1>(ma, mb, P, st);
-    case 642: return launch_conv<64, 2>(ma, mb, P, st);
-    case 1281: return launch_conv<128, 1>(ma, mb, P, st);
-    case 1282: return launch_conv<128, 2>(ma, mb, P, st);
-    case 2561: return launch_conv<256, 1>(ma, mb, P, st);
+  switch ((bn * 10 + mt) * 10 + t.cg) {
+    case 3211: return launch_conv<32, 1, 1>(ma, mb, P, st);
+    case 3221: return launch_conv<32, 2, 1>(ma, mb, P, st);
+    case 6411: return launch_conv<64, 1, 1>(ma, mb, P, st);
+    case 6421: return launch_conv<64, 2, 1>(ma, mb, P, st);
+    case 12811: return launch_conv<128, 1, 1>(ma, mb, P, st);
+    case 12821: return launch_conv<128, 2, 1>(ma, mb, P, st);
+    case 25611: return launch_conv<256, 1, 1>(ma, mb, P, st);
+    case 12812: return launch_conv<128, 1, 2>(ma, mb, P, st);
+    case 12822: return launch_conv<128, 2, 2>(ma, mb, P, st);
+    case 25612: return launch_conv<256, 1, 2>(ma, mb, P, st);
   }
-  return eadgan_set_error(EADGAN_ERR_UNSUPPORTED, "tc conv: unsupported BLOCK_N %d", bn);
+  return eadgan_set_error(EADGAN_ERR_UNSUPPORTED, "tc conv: unsupported tile configuration BLOCK_N %d, MT %d, cta_group %d",
+                          bn, mt, t.cg);
 }
 
 // BLOCK_N: 256 halves the A re-reads and the smem traffic per MAC; keep 128 while the tile count is too
@@ -1090,7 +1273,8 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
   EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_fprop: output map %dx%d must be a power of two <= 128 wide", p, q);
   const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
-  const int bn = pick_bn_tiles(d->k, m_tiles);
+  const TileCfg tcfg = pick_cfg(d->k, m_tiles, 1, true);
+  const int bn = tcfg.bn;
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_fprop: k=%d must be a multiple of 32", d->k);
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = d->c; P.qblocks = 2 * d->c / 64; P.nkb = 8 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
@@ -1100,8 +1284,8 @@ extern "C" int eadgan_tc_fprop(const eadgan_tc_desc* d, const void* x_pad, const
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_fprop: want_stats without stats");
   CUtensorMap ma, mb;
   if (int e = map_big_s2d(&ma, x_pad, d->n, d->c, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
-  if (int e = map_matrix(&mb, w_packed, d->k, (uint64_t)16 * d->c, bn)) return e;
-  return dispatch_conv(bn, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
+  if (int e = map_matrix(&mb, w_packed, d->k, (uint64_t)16 * d->c, bn / tcfg.cg)) return e;
+  return dispatch_conv(tcfg, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
 }
 
 extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, const void* w_packed, const float* bias,
@@ -1116,7 +1300,8 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED,
              "tc_dgrad: small map %dx%d must be a power of two <= 128 wide", p, q);
   const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
-  const int bn = pick_bn_tiles(d->c, 4 * m_tiles);
+  const TileCfg tcfg = pick_cfg(d->c, m_tiles, 4, true);
+  const int bn = tcfg.bn;
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
   P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = (d->k + 63) / 64; P.nkb = 4 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
@@ -1130,12 +1315,12 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_dgrad: want_stats without stats");
   CUtensorMap ma, mb;
   if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, P.Tw, P.Th, P.Tb)) return e;
-  if (int e = map_matrix(&mb, w_packed, (uint64_t)4 * d->c, (uint64_t)4 * d->k, bn)) return e;
-  return dispatch_conv(bn, ma, mb, P, m_tiles, d->c, 4, (cudaStream_t)stream);
+  if (int e = map_matrix(&mb, w_packed, (uint64_t)4 * d->c, (uint64_t)4 * d->k, bn / tcfg.cg)) return e;
+  return dispatch_conv(tcfg, ma, mb, P, m_tiles, d->c, 4, (cudaStream_t)stream);
 }
 
 namespace {
-int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
+int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits, int* cg) {
   const int p = d->h / 2, q = d->w / 2;
   // dy channel boxes past k are zero-filled by TMA and the matching partial rows are never read
   EG_REQUIRE(d->k % 32 == 0, EADGAN_ERR_UNSUPPORTED, "tc_wgrad: k=%d must be a multiple of 32", d->k);
@@ -1148,11 +1333,14 @@ int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
   P->Ktot = 16 * d->c;
   P->steps_total = ((d->n + P->Tb - 1) / P->Tb) * P->tiles_y;
   *bn = (P->Ktot % 256 == 0) ? 256 : (P->Ktot % 128 == 0 ? 128 : 64);
-  const int tiles = (P->Ktot / *bn) * ((d->k + 127) / 128);
+  // CTA pairs (256 ko rows per tile, see WgCfg) when there are whole 256-row tiles and a long reduction
+  *cg = (*bn == 256 && d->k % 256 == 0 && P->steps_total >= 256) ? 2 : 1;
+  if (const char* e = getenv("EADGAN_TC_CG")) { if (*bn == 256 && d->k % 256 == 0 && (atoi(e) == 1 || atoi(e) == 2)) *cg = atoi(e); }
+  const int tiles = (P->Ktot / *bn) * ((d->k + 127) / 128) / *cg;
   // split of the pixel reduction: one CTA per (tile, split) and one CTA per SM at a time, so the kernel runs in
   // waves of sm_count CTAs.  Pick the split count minimising  waves * steps_per_split  (tensor time, a 64-pixel
   // step of a 128 x bn tile is bn*2 clocks) plus the fp32 partial-sum traffic (written once, read once).
-  const int sms = eg_sm_count();
+  const int sms = eg_sm_count() / *cg;   // concurrently running CTAs (CTA pairs)
   const int max_s = (P->steps_total + 7) / 8;
   const int k_pad = ((d->k + 127) / 128) * 128;
   double best = 1e300;
@@ -1171,22 +1359,25 @@ int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits) {
   return 0;
 }
 
-template <int BN>
+template <int BN, int CG = 1>
 int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& P, dim3 grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(tc_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgCfg<BN>::SMEM));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  if (int e = opt_in_smem(tc_wgrad_kernel<BN, CG>, WgCfg<BN, CG>::SMEM, opted)) return e;
   // `grid` is the logical item space (kk tiles, ko tiles, splits); the launch is one CTA per SM at most, every
   // CTA running the same number of items (+-1)
   WgParams Q = P;
   Q.kk_tiles = (int)grid.x; Q.ko_tiles = (int)grid.y; Q.splits = (int)grid.z;
   const int total = Q.kk_tiles * Q.ko_tiles * Q.splits;
-  const int sms = eg_sm_count();
-  const int waves = (total + sms - 1) / sms;
-  const int ctas = (total + waves - 1) / waves;
-  tc_wgrad_kernel<BN><<<ctas, 192, WgCfg<BN>::SMEM, st>>>(mdy, mx, Q);
+  const int units = eg_sm_count() / CG;
+  const int waves = (total + units - 1) / units;
+  const int ctas = ((total + waves - 1) / waves) * CG;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ctas); cfg.blockDim = dim3(192); cfg.dynamicSmemBytes = WgCfg<BN, CG>::SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CG == 2 ? 1 : 0;
+  EG_CUDA(cudaLaunchKernelEx(&cfg, tc_wgrad_kernel<BN, CG>, mdy, mx, Q));
   EG_LAUNCH_CHECK("tc_wgrad_kernel");
   return 0;
 }
@@ -1195,8 +1386,8 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& 
 extern "C" size_t eadgan_tc_workspace_bytes(const eadgan_tc_desc* d, int direction) {
   if (direction != 2 || !d) return 0;
   WgParams P{};
-  int bn = 0, splits = 0;
-  if (wgrad_plan(d, &P, &bn, &splits) != 0) return 0;
+  int bn = 0, splits = 0, cg = 1;
+  if (wgrad_plan(d, &P, &bn, &splits, &cg) != 0) return 0;
   const int k_pad = ((d->k + 127) / 128) * 128;
   return (size_t)splits * k_pad * (size_t)P.Ktot * sizeof(float);
 }
@@ -1206,8 +1397,8 @@ extern "C" int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const
   if (int e = check_tc(d, "tc_wgrad")) return e;
   EG_REQUIRE(x_pad && dy_pad && dw && workspace, EADGAN_ERR_INVALID, "tc_wgrad: NULL pointer");
   WgParams P{};
-  int bn = 0, splits = 0;
-  if (int e = wgrad_plan(d, &P, &bn, &splits)) return e;
+  int bn = 0, splits = 0, cg = 1;
+  if (int e = wgrad_plan(d, &P, &bn, &splits, &cg)) return e;
   const int k_pad = ((d->k + 127) / 128) * 128;
   const size_t need = (size_t)splits * k_pad * (size_t)P.Ktot * sizeof(float);
   EG_REQUIRE(ws_bytes >= need, EADGAN_ERR_WORKSPACE, "tc_wgrad: workspace %zu < %zu bytes", ws_bytes, need);
@@ -1218,13 +1409,13 @@ extern "C" int eadgan_tc_wgrad(const eadgan_tc_desc* d, const void* x_pad, const
   CUtensorMap mdy, mx;
   if (int e = map_small(&mdy, dy_pad, d->n, d->k, P.p, P.q, P.Tw, P.Th, P.Tb)) return e;
   if (int e = map_big_s2d(&mx, x_pad, d->n, d->c, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
-  dim3 grid(P.Ktot / bn, k_pad / 128, splits);
+  dim3 grid(P.Ktot / bn, k_pad / (128 * cg), splits);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   switch (bn) {
     case 64: rc = launch_wgrad<64>(mdy, mx, PK, grid, st); break;
     case 128: rc = launch_wgrad<128>(mdy, mx, PK, grid, st); break;
-    default: rc = launch_wgrad<256>(mdy, mx, PK, grid, st); break;
+    default: rc = cg == 2 ? launch_wgrad<256, 2>(mdy, mx, PK, grid, st) : launch_wgrad<256>(mdy, mx, PK, grid, st); break;
   }
   if (rc) return rc;
   const int c_real = (d->c_real > 0 && d->c_real < d->c) ? d->c_real : d->c;
@@ -1237,14 +1428,15 @@ extern "C" int eadgan_tc_gemm(const void* a_bf16, const void* b_bf16, float* c_f
                               void* stream) {
   EG_REQUIRE(a_bf16 && b_bf16 && c_f32 && m > 0 && n > 0 && kk > 0, EADGAN_ERR_INVALID, "tc_gemm: bad arguments");
   EG_REQUIRE(kk % 64 == 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: K=%d must be a multiple of 64", kk);
-  const int bn = pick_bn_tiles(n, (m + 127) / 128);
+  const TileCfg tcfg = pick_cfg(n, (m + 127) / 128, 1, true);
+  const int bn = tcfg.bn;
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_gemm: N=%d must be a multiple of 32", n);
   TcParams P{};
   P.mode = MODE_GEMM; P.nkb = kk / 64; P.gemm_m = m; P.gemm_n = n; P.out = c_f32; P.N_total = n; P.n_store = n;
   CUtensorMap ma, mb;
   if (int e = map_matrix(&ma, a_bf16, m, kk, 128)) return e;
-  if (int e = map_matrix(&mb, b_bf16, n, kk, bn)) return e;
-  return dispatch_conv(bn, ma, mb, P, (m + 127) / 128, n, 1, (cudaStream_t)stream);
+  if (int e = map_matrix(&mb, b_bf16, n, kk, bn / tcfg.cg)) return e;
+  return dispatch_conv(tcfg, ma, mb, P, (m + 127) / 128, n, 1, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1302,7 +1494,8 @@ extern "C" int eadgan_tc_dense_gather(const void* y_pad, const void* w_rows, con
   CUtensorMap ma, mb;
   if (int e = map_pad6(&ma, y_pad, n, C, 128)) return e;
   if (int e = map_matrix(&mb, w_rows, 32, (uint64_t)16 * C, 32)) return e;
-  if (int e = dispatch_conv(32, ma, mb, P, (n + 127) / 128, 32, GATHER_SPLITS, (cudaStream_t)stream)) return e;
+  if (int e = dispatch_conv(pick_cfg(32, (n + 127) / 128, GATHER_SPLITS, false, 32), ma, mb, P, (n + 127) / 128, 32,
+                            GATHER_SPLITS, (cudaStream_t)stream)) return e;
   dense_gather_sum_kernel<<<(n * m_real + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, bias, n,
                                                                                       m_real, out);
   EG_LAUNCH_CHECK("dense_gather_sum_kernel");
@@ -1323,7 +1516,8 @@ extern "C" int eadgan_tc_dense_scatter(const void* a_bf16, const void* w_cols, c
   CUtensorMap ma, mb;
   if (int e = map_matrix(&ma, a_bf16, n, m_pad, 128)) return e;
   if (int e = map_matrix(&mb, w_cols, (uint64_t)16 * C, m_pad, 128)) return e;
-  return dispatch_conv(128, ma, mb, P, (n + 127) / 128, 16 * C, 1, (cudaStream_t)stream);
+  return dispatch_conv(pick_cfg(16 * C, (n + 127) / 128, 1, false, 128), ma, mb, P, (n + 127) / 128, 16 * C, 1,
+                       (cudaStream_t)stream);
 }
 
 extern "C" size_t eadgan_tc_dense_wgrad_workspace(int C, int m_pad) {
@@ -1512,8 +1706,8 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           uint8_t* sa = smem + stage * THIN_STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], THIN_STAGE_BYTES);
           // padded small map rows r0 .. r0+3  =  image rows r0-1 .. r0+2 (row -1 / row p are the zero halo)
-          tma_load_4d(sa, &map_a, &full_bar[stage], kb * BLOCK_K, 1, r0, b);
-          tma_load_2d(sa + A_BYTES, &map_b, &full_bar[stage], kb * BLOCK_K, 0);
+          tma_load_4d<1>(sa, &map_a, smem_u32(&full_bar[stage]), kb * BLOCK_K, 1, r0, b);
+          tma_load_2d<1>(sa + A_BYTES, &map_b, smem_u32(&full_bar[stage]), kb * BLOCK_K, 0);
           if (++stage == THIN_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -1668,6 +1862,7 @@ extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, 
   const int m_tiles = ((d->n + P.Tb - 1) / P.Tb) * (p / P.Th);
   const int bn = pick_bn(d->k);
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_fprop: k=%d must be a multiple of 32", d->k);
+  const TileCfg tcfg = pick_cfg(d->k, m_tiles, 1, false, bn);
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = 4; P.qblocks = 1; P.nkb = 1;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
@@ -1677,7 +1872,7 @@ extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, 
   CUtensorMap ma, mb;
   if (int e = map_thin(&ma, r_buf, d->n, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
   if (int e = map_matrix(&mb, w_packed, d->k, 64, bn)) return e;
-  return dispatch_conv(bn, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
+  return dispatch_conv(tcfg, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
 }
 
 namespace {
@@ -1749,11 +1944,8 @@ extern "C" int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad,
   CUtensorMap ma, mb;
   if (int e = map_small(&ma, dy_pad, d->n, d->k, p, q, 32, 4, 1)) return e;
   if (int e = map_matrix(&mb, w_packed, 64, (uint64_t)d->k, 64)) return e;
-  static bool attr_set = false;
-  if (!attr_set) {
-    EG_CUDA(cudaFuncSetAttribute(tc_thin_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, THIN_SMEM));
-    attr_set = true;
-  }
+  static std::atomic<uint64_t> opted{0};
+  if (int e = opt_in_smem(tc_thin_dgrad_kernel, THIN_SMEM, opted)) return e;
   const int total = d->n * (p / 2);
   const int sms = eg_sm_count();
   const int waves = (total + sms - 1) / sms;

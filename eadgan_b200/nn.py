@@ -166,16 +166,24 @@ class Sequential(_TorchSequential):
         if out is not None:
             return out
         mods = list(self._modules.values())
+        log = None
+        if chain.gate_log is not None:     # tests only (tests/gates.py): record the ReLU / LeakyReLU gates of this forward
+            log = []
+            chain.gate_log.append((self, log))
         i = 0
         while i < len(mods):
             m = mods[i]
             nxt = mods[i + 1] if i + 1 < len(mods) else None
             if isinstance(m, _FUSABLE) and isinstance(nxt, _Act) and _plain(nxt):
                 x = m(x, act=nxt.act())
+                gated = nxt
                 i += 2
             else:
                 x = m(x)
+                gated = m if isinstance(m, _Act) else None
                 i += 1
+            if log is not None and gated is not None and gated.act()[0] in (ACT_RELU, ACT_LRELU):
+                log.append(x.detach() > 0)
         return x
 
 

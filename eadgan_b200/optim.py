@@ -26,7 +26,11 @@ class Adam(torch.optim.Optimizer):
         if not 0.0 <= lr or not 0.0 <= eps or not 0.0 <= betas[0] < 1.0 or not 0.0 <= betas[1] < 1.0:
             raise ValueError("Invalid Adam hyper-parameter")
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False))
-        self._dp = None  # set by eadgan_b200.parallel.attach()
+        # data parallelism: when a DP state exists (parallel.init / init_from_env ran first, as under
+        # ``torchrun -m eadgan_b200.run script.py``), every Adam all-reduces the gradients of its own parameter set
+        # in step(); parallel.attach() does the same explicitly for optimisers built before init
+        from . import parallel
+        self._dp = parallel.get()
         self._step_dev = None       # device int64 step counter (CUDA-graph capture, eadgan_b200.graph)
         self._captured = None       # parameters stepped by the captured step() (their python "step" mirrors)
 
@@ -96,12 +100,16 @@ class Adam(torch.optim.Optimizer):
                     self._launch(ps, gs, ms, vs, group, t, gscale)
                     ps, gs, ms, vs = [], [], [], []
                     t = st["step"]
+                p._eadgan_stepped = L.weights_epoch + 1   # spectral-norm results prefetched before this step are stale
                 ps.append(p)
                 gs.append(g if g.is_contiguous() else g.contiguous())
                 ms.append(st["exp_avg"])
                 vs.append(st["exp_avg_sq"])
             if ps:
                 self._launch(ps, gs, ms, vs, group, t, gscale, self._step_dev if capturing else None)
+        if not capturing and self._step_dev is not None:
+            # an eager step between graph replays: the device counter the captured step() reads must advance too
+            call("eadgan_adam_advance", C.c_void_p(self._step_dev.data_ptr()), stream())
         L.bump_weights_epoch()   # parameters changed through raw pointers: packed-weight caches are stale
         return loss
 

@@ -72,7 +72,7 @@ class DataParallel:
                 plan["where"][p] = (bi, len(views) - 1)
                 off += p.numel()
             plan["buckets"].append({"params": ps, "flat": flat, "views": views, "pending": 0, "work": None,
-                                    "filled": set()})
+                                    "filled": set(), "dirty": False})
         self._plans[id(opt)] = plan
         for p in params:
             if p not in self._hooks_installed:
@@ -86,6 +86,7 @@ class DataParallel:
         for b in plan["buckets"]:
             b["filled"].clear()
             b["work"] = None
+            b["dirty"] = False
         self._armed = plan
 
     def _on_grad(self, p):
@@ -97,8 +98,9 @@ class DataParallel:
             return  # gradient of a parameter this phase's optimiser does not own: never communicated
         b = plan["buckets"][loc[0]]
         if p in b["filled"]:
-            # second accumulation into the same .grad in one phase: fall back to reduce-at-step
-            b["work"] = "dirty"
+            # second accumulation into the same .grad in one phase: fall back to reduce-at-step (the in-flight
+            # all-reduce, if any, is waited for there before ``flat`` is rewritten)
+            b["dirty"] = True
             return
         b["views"][loc[1]].copy_(p.grad)
         b["filled"].add(p)
@@ -118,13 +120,19 @@ class DataParallel:
         plan = self._plan(opt)
         out = {}
         for b in plan["buckets"]:
-            if b["work"] is None or b["work"] == "dirty":
+            if b["work"] is None or b["dirty"]:
+                if b["work"] is not None:
+                    # an all-reduce launched before the second accumulation is still writing ``flat``
+                    b["work"].wait()
+                    if self.comm_stream is not None:
+                        torch.cuda.current_stream().wait_stream(self.comm_stream)
                 for p, v in zip(b["params"], b["views"]):
                     if p.grad is not None:
                         v.copy_(p.grad)
                     else:
                         v.zero_()
                 b["work"] = None
+                b["dirty"] = False
                 self._launch(b)
         for b in plan["buckets"]:
             b["work"].wait()
@@ -148,6 +156,12 @@ def attach(*optimizers):
         return
     for o in optimizers:
         o._dp = _state
+
+
+def detach(*optimizers):
+    """the given optimisers step on local gradients only (single-device reference runs inside a DP process)"""
+    for o in optimizers:
+        o._dp = None
 
 
 def init(rank, world_size, device, backend=None, **kw):

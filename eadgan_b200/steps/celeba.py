@@ -99,14 +99,23 @@ class CelebAStep:
         # D's weights do not change until opt_D.step(): the power iterations of its next three forwards (D(gen) below,
         # then the two of phase D) depend only on the weights and on u / v, so they are issued now, on a side stream,
         # and overlap G's forward instead of preceding every D conv stack on the critical path
-        chain.prefetch_spectral_norm(D.main, 3)
+        # Phase G differentiates THROUGH D but only opt_G steps: D is frozen for it, so D's weight gradients (which
+        # the reference computes and then discards at :353) are never launched.  The weight tensors W / sigma are
+        # produced by the prefetch, hence one prefetch with D frozen (phase G's forward) and two with D trainable
+        chain.clear_prefetch(D.main)          # leftovers of an aborted step, if any
+        chain.set_trainable(D, False)
+        chain.prefetch_spectral_norm(D.main, 1)
+        chain.set_trainable(D, True)
+        chain.prefetch_spectral_norm(D.main, 2)
 
         # phase G -- :334-345
         self.opt_G.zero_grad()
+        chain.set_trainable(D, False)
         gen = G(z, onehot, code)
         _, _, validity = D(gen)
         g_loss = self.bce(validity, valid)
         g_loss.backward()
+        chain.set_trainable(D, True)
         self._snap(self.opt_G, record, "G")
         self.opt_G.step()
         self._after(self.opt_G, record)

@@ -72,6 +72,8 @@ class ColoredDSpritesStep(DSpritesStep):
             o.scatter_(1, labels.view(-1, 1), 1.0)
             return o
 
+        chain.clear_prefetch(D.conv_block)          # leftovers of an aborted step, if any
+        chain.clear_prefetch(E.conv_block)
         chain.prefetch_spectral_norm(D.conv_block, 2)      # see steps/dsprites.py
         chain.prefetch_spectral_norm(E.conv_block, 3)
 
@@ -89,6 +91,9 @@ class ColoredDSpritesStep(DSpritesStep):
         self._after(self.opt_D, record)
         if after_phase is not None:
             after_phase(0)
+        # the info phase differentiates THROUGH D (g_loss) but opt_info owns only G and E: D is frozen for it, its
+        # weight gradients (computed and never read by the reference) are not launched
+        chain.set_trainable(D, False)
         chain.prefetch_spectral_norm(D.conv_block, 1)      # D(gen) of the info phase
 
         # phase info -- rp_color.py:444-516
@@ -107,6 +112,7 @@ class ColoredDSpritesStep(DSpritesStep):
         total = cat_loss + cont_loss + affine_loss + rel_cat_loss + g_loss
         self.opt_info.zero_grad()
         total.backward()
+        chain.set_trainable(D, True)
         self._snap(self.opt_info, record, "info")
         self.opt_info.step()
         self._after(self.opt_info, record)

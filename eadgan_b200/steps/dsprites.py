@@ -139,6 +139,8 @@ class DSpritesStep:
 
         # spectral-norm power iterations of the coming forwards, issued early on a side stream (they depend only on
         # weights that stay fixed until the owning optimiser steps): D twice in phase D, E three times in phase info
+        chain.clear_prefetch(D.conv_block)          # leftovers of an aborted step, if any
+        chain.clear_prefetch(E.conv_block)
         chain.prefetch_spectral_norm(D.conv_block, 2)
         chain.prefetch_spectral_norm(E.conv_block, 3)
 
@@ -156,6 +158,9 @@ class DSpritesStep:
         self._after(self.opt_D, record)
         if after_phase is not None:
             after_phase(0)
+        # the info phase differentiates THROUGH D (g_loss) but opt_info owns only G and E: D is frozen for it, its
+        # weight gradients (computed and never read by the reference) are not launched
+        chain.set_trainable(D, False)
         chain.prefetch_spectral_norm(D.conv_block, 1)      # D(gen) of the info phase
 
         # phase info -- rp.py:424-482
@@ -174,6 +179,7 @@ class DSpritesStep:
         total = cat_loss + cont_loss + affine_loss + g_loss + rel_cat_loss
         self.opt_info.zero_grad()
         total.backward()
+        chain.set_trainable(D, True)
         self._snap(self.opt_info, record, "info")
         self.opt_info.step()
         self._after(self.opt_info, record)

@@ -21,8 +21,12 @@ _pool_enabled = True
 capture_births = None   # list while a CUDA-graph capture is running (eadgan_b200.graph): buffers first created inside it
 
 
-def _recycle(key, base):
-    _pool.setdefault(key, []).append(base)
+_pool_gen = 0           # bumped by clear_pool(): buffers handed out before it are NOT recycled into the new pool
+
+
+def _recycle(key, base, gen):
+    if gen == _pool_gen:
+        _pool.setdefault(key, []).append(base)
 
 
 def alloc_padded(n, h, w, c, device, zero_interior=False, c_real=None):
@@ -44,13 +48,21 @@ def alloc_padded(n, h, w, c, device, zero_interior=False, c_real=None):
             # in the pool and eager code (or another capture) may pick it up before this graph ever runs.
             capture_births.append(base)
     t = base.view(shape)
-    weakref.finalize(t, _recycle, key, base)
+    weakref.finalize(t, _recycle, key, base, _pool_gen)
     return t
 
 
 def clear_pool():
-    """drop every pooled buffer (frees the memory back to torch's allocator)"""
+    """drop every pooled buffer and workspace (frees the memory back to torch's allocator); buffers still in use are
+    dropped when they die instead of being recycled.  eadgan_b200.graph.GraphedStep calls this on both sides of a
+    capture, so that everything a captured step touches is allocated from -- and stays inside -- the graph's
+    private memory pool: nothing a later eager call (or another capture) can free or reuse under a live graph."""
+    global _pool_gen
+    _pool_gen += 1
     _pool.clear()
+    _ws_cache.clear()
+    from . import functional as Fn
+    Fn._ws_cache.clear()
 
 
 def interior(xp):

@@ -365,6 +365,17 @@ int eadgan_relcode_fwd(int mode, const float* real, long long real_stride, const
 int eadgan_relcode_bwd(int mode, const float* g, const float* jac, int n, float* d_real, float* d_trans,
                        void* stream);
 
+/* ------------------------------------------------------------------------- */
+/* Device-side sampling of the per-iteration latent draws: replaces the host
+ * NumPy sampling + H2D copies of celebA/EAD-GAN_celebA.py:308-318, dSprites/rp.py:389-396,424-434.
+ * Philox4x32-10, counter = (group of 4 elements of the GLOBAL [*, cols] array, stream_id, step), key = seed:
+ * rows [row0, row0+rows) of a sharded batch are exactly the rows a single device draws.
+ * kind 0: uniform [lo, hi) fp32; 1: standard normal fp32 (Box-Muller); 2: integers in [0, n) as int64.
+ * step: *step_dev when step_dev != NULL (CUDA-graph replay), else step_host.  See csrc/sample.cu.           */
+/* ------------------------------------------------------------------------- */
+int eadgan_philox(int kind, unsigned long long seed, const int64_t* step_dev, long long step_host, int stream_id,
+                  long long row0, long long rows, long long cols, float lo, float hi, int n, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

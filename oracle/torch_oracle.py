@@ -181,8 +181,10 @@ def _state(G, D):
             "D": {k: v.detach().clone() for k, v in D.state_dict().items()}}
 
 
-def step_celeba(st, imgs, draws, record=True):
-    """One iteration of celebA/EAD-GAN_celebA.py:297-401 on batch ``imgs`` [B,3,64,64]."""
+def step_celeba(st, imgs, draws, record=True, after_phase=None):
+    """One iteration of celebA/EAD-GAN_celebA.py:297-401 on batch ``imgs`` [B,3,64,64].
+    ``after_phase(i)`` (parity tests only) runs after the optimiser step of phase i = 0, 1: it lets a test restart
+    the next phase from another run's state, exactly like the hook of eadgan_b200.steps.celeba.CelebAStep."""
     G, D = st["G"], st["D"]
     dev, dt = imgs.device, imgs.dtype
     B = imgs.shape[0]
@@ -210,6 +212,8 @@ def step_celeba(st, imgs, draws, record=True):
     if record:
         rec["phases"][-1]["params_after"] = _params(st["opt_G"])
         rec["phases"][-1]["state_after"] = _state(G, D)
+    if after_phase is not None:
+        after_phase(0)
 
     # ---- phase D  (:353-366)
     st["opt_D"].zero_grad()
@@ -225,6 +229,8 @@ def step_celeba(st, imgs, draws, record=True):
     if record:
         rec["phases"][-1]["params_after"] = _params(st["opt_D"])
         rec["phases"][-1]["state_after"] = _state(G, D)
+    if after_phase is not None:
+        after_phase(1)
 
     # ---- phase info  (:375-401)
     st["opt_info"].zero_grad()

@@ -58,6 +58,19 @@ def _worker(rank, world, port, overlap, q):
             tot = gs if tot is None else [t + g for t, g in zip(tot, gs)]
         refs[name] = tot
     ok = all(torch.allclose(u, v, rtol=1e-5, atol=1e-6) for k in refs for u, v in zip(results[k], refs[k]))
+    # two backward passes into the same optimiser's gradients within one phase (the all-reduce launched
+    # after the first accumulation must be waited for, then the buckets are re-reduced from the final .grad values)
+    for p in a + b:
+        p.grad = None
+    dp.arm(opt_ab)
+    loss_fn(x).backward()
+    loss_fn(x).backward()
+    red = dp.reduce(opt_ab)
+    ok = ok and all(torch.allclose(red[p], 2 * r, rtol=1e-5, atol=1e-6) for p, r in zip(a + b, refs["ab"]))
+    # an Adam built while a data-parallel state exists all-reduces in step() without an explicit attach()
+    # (``torchrun -m eadgan_b200.run script.py`` builds its optimisers inside the unmodified script)
+    from eadgan_b200.optim import Adam
+    ok = ok and Adam(a, lr=1e-3)._dp is dp
     # SyncBN helper
     t = torch.tensor([1.0 + rank, 2.0], dtype=torch.float64)
     dp.allreduce_sum_(t)

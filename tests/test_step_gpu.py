@@ -76,11 +76,10 @@ def test_celeba_state_dict_roundtrip(cuda):
 
 @pytest.mark.parametrize("B", [16, 64])
 def test_celeba_step_bf16(cuda, B):
-    """bf16 tcgen05 chain.  Losses: north_star tolerance 2e-2.  Gradients: any two bf16 evaluations of these
-    nets flip ~0.1-0.3 % of the LeakyReLU(0.1)/ReLU gates against fp32 (a pre-activation within bf16 rounding
-    of 0), which is a ~5-10 % L2 perturbation of every upstream gradient whatever the kernel -- so the
-    whole-step check is direction (cosine) and L2; the 2e-2 max bound is carried per layer on identical
-    inputs by tests/test_tc_gpu.py and on gate-insensitive stacks by tests/test_chain_gpu.py."""
+    """bf16 tcgen05 chain, UN-forced: losses to north_star's 2e-2; gradients by direction and L2 against the fp64
+    oracle on its own branch (any two bf16 evaluations of these nets flip ~0.1-0.3 % of the LeakyReLU(0.1) / ReLU
+    gates against fp64; the per-tensor 2e-2 bound is asserted by test_celeba_step_bf16_forced_gates below, where
+    both runs are on the same piecewise-linear branch)."""
     ref, rec, losses, st, ours = U.run_pair(cuda, B, "bf16")
     for k in ("g_loss", "d_loss", "info_loss"):
         assert abs(losses[k] - ref["losses"][k]) <= 2e-2 * max(1.0, abs(ref["losses"][k])), (k, losses, ref["losses"])
@@ -94,8 +93,73 @@ def test_celeba_step_bf16(cuda, B):
                 assert mx <= 0.15, (ph, n, mx)      # [3]-element bias, normalised by its layer's weight gradient
             else:
                 assert cs >= 0.95, (ph, n, cs)
-                assert l2 <= 0.35, (ph, n, l2)
+                assert l2 <= (0.15 if B >= 64 else 0.2), (ph, n, l2)    # a flipped gate weighs 1/B of the batch mean
     so, sr = ours.G.state_dict(), st["G"].state_dict()
     for k in sr:
         if "running" in k:
             assert rel_err(so[k], sr[k]) <= 2e-2, k
+
+
+def _assert_forced(out, tol, what):
+    ours_names = U.grad_names(out["step"])
+    ref = out["forced"][0]
+    for k in ("g_loss", "d_loss", "info_loss"):
+        assert abs(out["losses"][k] - ref["losses"][k]) <= tol * max(1.0, abs(ref["losses"][k])), (what, k)
+    worst = 0.0
+    for ph in range(3):
+        errs = U.phase_errors(ours_names[ph], out["ours"][ph]["grads"], ref["phases"][ph]["grads"])
+        for n, (mx, l2, cs) in errs.items():
+            assert mx <= tol, (what, ph, n, mx, l2)
+            worst = max(worst, mx)
+    return worst
+
+
+@pytest.mark.parametrize("B", [16, 64])
+def test_celeba_step_bf16_forced_gates(cuda, B):
+    """north_star's bf16 bound on EVERY gradient tensor of EVERY phase: max|ours - oracle| / max|oracle| <= 2e-2
+    with the fp64 oracle evaluated on the activation gates of our run (tests/gates.py)."""
+    import gates
+    out = gates.celeba_forced(cuda, B, "bf16")
+    assert out["flips"] <= 0.01 * out["gates"]          # the forced branch is the oracle's own up to ~0.1-0.3 %
+    worst = _assert_forced(out, 2e-2, f"bf16 B={B}")
+    print(f"bf16 B={B}: gate flips {out['flips']} of {out['gates']}, worst tensor-normalised gradient error {worst:.2e}")
+
+
+def test_celeba_step_fp32_relative_to_stock_fp32(cuda):
+    """with fp64 as referee, OUR fp32 error may not exceed 3x stock torch fp32's own
+    error (cuDNN / cuBLAS, TF32 off) on the same inputs, tensor by tensor -- all three runs on the same gates."""
+    import gates
+    out = gates.celeba_forced(cuda, 8, "fp32", oracle_dtypes=(torch.float64, torch.float32))
+    ref64, ref32 = out["forced"]
+    for k in ("g_loss", "d_loss", "info_loss"):
+        assert abs(out["losses"][k] - ref64["losses"][k]) <= 2e-5 * max(1.0, abs(ref64["losses"][k])), k
+    names = U.grad_names(out["step"])
+    for ph in range(3):
+        e_ours = U.phase_errors(names[ph], out["ours"][ph]["grads"], ref64["phases"][ph]["grads"])
+        e_ref = U.phase_errors(names[ph], ref32["phases"][ph]["grads"], ref64["phases"][ph]["grads"])
+        for n in e_ours:
+            assert e_ours[n][0] <= max(3.0 * e_ref[n][0], 1e-5), (ph, n, e_ours[n][0], e_ref[n][0])
+
+
+def test_phase_g_skips_discriminator_weight_gradients(cuda):
+    """phase G differentiates through D with D frozen: D's parameters receive no gradient
+    there, the generator's gradients are unchanged, and D is trainable again in phases D / info."""
+    import os
+    import numpy as np
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = "bf16"
+    step = CelebAStep(seed=0, device=cuda)
+    imgs = O.synth_celeba_images(8, 0).to(cuda)
+    d = O.sample_celeba(np.random.RandomState(0), 8)
+    seen = {}
+
+    def after(i):
+        seen[i] = [p.grad is None for p in step.D.parameters()]
+
+    rec = []
+    step(imgs, d["z"].to(cuda), d["code"].to(cuda), d["labels"].to(cuda), record=rec, after_phase=after)
+    assert all(seen[0])                      # after phase G: no D gradient was produced
+    assert not any(seen[1])                  # after phase D: every D parameter has one
+    assert all(p.requires_grad for p in step.D.parameters())
+    assert all(g is not None for g in rec[2]["grads"])      # the info phase owns G and D

@@ -188,3 +188,53 @@ def test_dense_layers(cuda, n):
     assert rel_err(tc.dense_wgrad(ah, yp, 19), gwh) <= 2e-3
     dxp = tc.dense_scatter(ah, tc.dense_pack(wh, 64, False), None, C, mask=yp, mask_act=ACT_LRELU, slope=0.1)
     assert rel_err(tc.from_padded(dxp), gy * torch.where(y > 0, 1.0, 0.1)) <= 1e-2
+
+
+# ---- cta_group::2 (CTA pairs): forced on through EADGAN_TC_CG so that small, ragged cases exercise the pair protocol
+# (odd numbers of M tiles -> the peer CTA of the last pair runs an all-out-of-range tile; one tile per pair; several)
+@pytest.fixture
+def pairs(monkeypatch):
+    monkeypatch.setenv("EADGAN_TC_CG", "2")
+
+
+PAIR_GEOS = [(4, 128, 32, 256), (3, 128, 32, 256), (9, 256, 16, 512), (16, 512, 8, 1024), (40, 256, 16, 256)]
+
+
+@pytest.mark.parametrize("mnk", [(256, 256, 64), (384, 256, 512), (300, 128, 256), (8192, 512, 1024), (77, 256, 128)])
+def test_gemm_cta_pairs(cuda, pairs, mnk):
+    from eadgan_b200 import tc
+    m, n, k = mnk
+    torch.manual_seed(0)
+    a = torch.randn(m, k, device=cuda).bfloat16()
+    b = torch.randn(n, k, device=cuda).bfloat16()
+    assert rel_err(tc.gemm(a, b), a.float() @ b.float().t()) <= 1e-4
+
+
+@pytest.mark.parametrize("geo", PAIR_GEOS)
+def test_conv_cta_pairs(cuda, pairs, geo):
+    """fprop / dgrad (+ BatchNorm statistics, + fused mask) / wgrad through the cta_group::2 kernels."""
+    from eadgan_b200 import tc
+    from eadgan_b200._lib import ACT_LRELU
+    n, c, h, k = geo
+    torch.manual_seed(8)
+    x = _bf(torch.randn(n, c, h, h, device=cuda))
+    w = _bf(torch.randn(k, c, 4, 4, device=cuda) * 0.05)
+    bk, bc = torch.randn(k, device=cuda), torch.randn(c, device=cuda)
+    ref = TF.leaky_relu(TF.conv2d(x, w, bk, stride=2, padding=1), 0.1)
+    xp = tc.to_padded(x)
+    out = tc.fprop(xp, tc.pack_w(w, None, "fprop"), bk, k, ACT_LRELU, 0.1, out_f32_nchw=True)
+    assert rel_err(out, ref) <= 2e-3
+    y = _bf(torch.randn(n, k, h // 2, h // 2, device=cuda))
+    yp = tc.to_padded(y)
+    reft = TF.conv_transpose2d(y, w, bc, stride=2, padding=1)
+    stats = torch.zeros(2 * c, device=cuda, dtype=torch.float64)
+    outt = tc.dgrad(yp, tc.pack_w(w, None, "dgrad"), bc, c, out_f32_nchw=True, stats=stats)
+    assert rel_err(outt, reft) <= 2e-3
+    assert rel_err(stats[:c], reft.double().sum((0, 2, 3))) <= 2e-3
+    assert rel_err(stats[c:], (reft.double() ** 2).sum((0, 2, 3))) <= 2e-3
+    refm = TF.conv_transpose2d(y, w, None, stride=2, padding=1) * torch.where(x > 0, 1.0, 0.1)
+    outm = tc.dgrad(yp, tc.pack_w(w, None, "dgrad"), None, c, mask=xp, mask_mode=ACT_LRELU, slope=0.1)
+    assert rel_err(tc.from_padded(outm), refm) <= 1e-2
+    wz = torch.zeros(k, c, 4, 4, device=cuda, requires_grad=True)
+    gw = torch.autograd.grad(TF.conv2d(x, wz, None, stride=2, padding=1), wz, y)[0]
+    assert rel_err(tc.wgrad(xp, yp), gw) <= 2e-3
