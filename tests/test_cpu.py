@@ -460,10 +460,27 @@ def test_benchmark_input_generator_equals_the_oracles():
     from oracle import torch_oracle as O
     for seed in (0, 1, 7):
         assert torch.equal(synthetic.celeba_images(5, seed), O.synth_celeba_images(5, seed))
+        assert torch.equal(synthetic.dsprites_images(6, seed), O.synth_dsprites_images(6, seed))
+        mine = synthetic.sample_celeba(np.random.RandomState(seed), 4)
+        ref = O.sample_celeba(np.random.RandomState(seed), 4)
+        assert all(torch.equal(a, ref[k]) for a, k in zip(mine, ("z", "code", "labels")))
     src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
     main_arm = src[src.index("def _main():"):]
-    # the product arm of the benchmark touches the oracle only inside cpu_reference() (the cpu_baseline leg)
+    # the product arm of the benchmark touches the oracle only inside cpu_reference() (the cpu_baseline leg) and
+    # parity_block() (the checker of the timed configuration, outside the timed region)
     assert "from oracle" not in main_arm and "import oracle" not in main_arm
+
+
+def test_philox_restatement_known_answers():
+    """oracle/philox_ref.py against the known-answer vectors of Philox4x32-10 (Random123 kat_vectors)."""
+    from oracle.philox_ref import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(np.array([ctr], dtype=np.uint32), key)[0]
+        assert tuple(int(x) for x in got) == want
 
 
 def test_affine_product_entry_points_have_no_cpu_fallback():
