@@ -101,6 +101,10 @@ _PROTOS = {
     "eadgan_f64_to_f32": [_P, _P, _L, _P],
     "eadgan_zero_halo": [_P, _I, _I, _I, _I, _P],
     "eadgan_stn_fwd": [_P, _P, _I, _I, _I, _I, _I, _P, _P],
+    "eadgan_affine_grid_fwd": [_P, _I, _I, _I, _P, _P],
+    "eadgan_affine_grid_bwd": [_P, _I, _I, _I, _P, _P],
+    "eadgan_grid_sample_fwd": [_P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P],
+    "eadgan_grid_sample_bwd": [_P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P, _P],
     "eadgan_relcode_dims": [_I, _P, _P],
     "eadgan_relcode_fwd": [_I, _P, C.c_longlong, _P, C.c_longlong, _I, _P, _P, _P],
     "eadgan_relcode_bwd": [_I, _P, _P, _I, _P, _P, _P],

@@ -15,7 +15,6 @@ from __future__ import annotations
 import math
 
 import torch
-import torch.nn.functional as TF
 
 from . import functional as Fn
 
@@ -92,13 +91,16 @@ def celeba_relative_code_torch(real_code, trans_code):
 
 def stn(img, theta23, padding_mode="border"):
     """transformation_2D.stn (celebA/EAD-GAN_celebA.py:149-153).  When no gradient is requested through it (every
-    consumed gradient of the training steps: the warped images are constants) this is one fused forward kernel;
-    otherwise the stock differentiable torch ops."""
+    consumed gradient of the training steps: the warped images are constants) this is ONE fused forward kernel;
+    otherwise the affine_grid and grid_sample kernels with their backward passes (csrc/glue.cu) -- never stock ATen."""
+    if not _fused(img, theta23):
+        raise RuntimeError("eadgan_b200.affine.stn: CUDA float32 tensors required (no CPU fallback)")
+    if padding_mode not in ("border", "zeros"):
+        raise RuntimeError("eadgan_b200.affine.stn: padding_mode must be 'border' or 'zeros'")
     needs_grad = torch.is_grad_enabled() and (img.requires_grad or theta23.requires_grad)
-    if _fused(img) and not needs_grad and padding_mode in ("border", "zeros"):
+    if not needs_grad:
         return Fn.stn_fwd(img, theta23, border=padding_mode == "border")
-    grid = TF.affine_grid(theta23, list(img.shape), align_corners=False)
-    return TF.grid_sample(img, grid, padding_mode=padding_mode, align_corners=False)
+    return Fn.grid_sample(img, Fn.affine_grid(theta23, tuple(img.shape)), padding_mode=padding_mode)
 
 
 # ---- dSprites (dSprites/utils_pxy.py, dSprites/utils_rp.py) -----------------------------------------------

@@ -255,6 +255,177 @@ extern "C" int eadgan_stn_fwd(const float* img, const float* theta, int n, int c
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// F.affine_grid / F.grid_sample as separate differentiable operators (align_corners = False, bilinear,
+// padding 'border' | 'zeros'): what the UNMODIFIED reference scripts call (transformation_2D.stn:
+// celebA/EAD-GAN_celebA.py:149-153; dSprites/rp.py:200-211; colored_dSprites/pxy_color.py:82-96 'zeros').
+// In rp.py their BACKWARD is on the executed path: the frozen Encoder_pxy is grad-tracked, so autograd runs
+// grid_sample's gradient w.r.t. the sampled image and w.r.t. the grid, and affine_grid's w.r.t. theta
+// (dSprites/rp.py:374-377,399-400).  Formulas follow ATen's grid_sampler_2d (bilinear) including the
+// clip_coordinates_set_grad rule of 'border' (zero coordinate gradient where the coordinate was clamped).
+// ---------------------------------------------------------------------------------------------------
+namespace {
+
+__global__ void __launch_bounds__(256) affine_grid_fwd_kernel(const float* __restrict__ theta, int n, int h, int w,
+                                                              float* __restrict__ grid) {
+  const int64_t total = (int64_t)n * h * w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % w), y = (int)((i / w) % h);
+    const float* t = theta + (i / ((int64_t)w * h)) * 6;
+    const float xn = (2.f * x + 1.f) / w - 1.f, yn = (2.f * y + 1.f) / h - 1.f;
+    reinterpret_cast<float2*>(grid)[i] = make_float2(fmaf(t[0], xn, fmaf(t[1], yn, t[2])), fmaf(t[3], xn, fmaf(t[4], yn, t[5])));
+  }
+}
+
+// d_theta[b][i][j] = sum over pixels of d_grid[b][y][x][i] * base_j,  base = (xn, yn, 1).  One block per image,
+// fixed-order tree reduction: deterministic.
+__global__ void __launch_bounds__(256) affine_grid_bwd_kernel(const float* __restrict__ dgrid, int h, int w,
+                                                              float* __restrict__ dtheta) {
+  __shared__ float red[6][256];
+  const int b = blockIdx.x;
+  float acc[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float2* g = reinterpret_cast<const float2*>(dgrid) + (int64_t)b * h * w;
+  for (int i = threadIdx.x; i < h * w; i += 256) {
+    const int x = i % w, y = i / w;
+    const float xn = (2.f * x + 1.f) / w - 1.f, yn = (2.f * y + 1.f) / h - 1.f;
+    const float2 d = g[i];
+    acc[0] += d.x * xn; acc[1] += d.x * yn; acc[2] += d.x;
+    acc[3] += d.y * xn; acc[4] += d.y * yn; acc[5] += d.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 6; ++j) red[j][threadIdx.x] = acc[j];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) red[j][threadIdx.x] += red[j][threadIdx.x + s];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x < 6) dtheta[b * 6 + threadIdx.x] = red[threadIdx.x][0];
+}
+
+struct Sample {            // bilinear footprint of one output pixel
+  int x0, y0;              // north-west corner (may be out of range)
+  float tx, ty;            // fractional offsets
+  float mx, my;            // d(source coordinate) / d(grid coordinate): size / 2, or 0 where 'border' clamped
+};
+__device__ __forceinline__ Sample locate(float gx, float gy, int h, int w, int border) {
+  Sample s;
+  float ix = ((gx + 1.f) * w - 1.f) * 0.5f, iy = ((gy + 1.f) * h - 1.f) * 0.5f;
+  s.mx = 0.5f * w; s.my = 0.5f * h;
+  if (border) {            // clip_coordinates_set_grad
+    if (ix <= 0.f) { ix = 0.f; s.mx = 0.f; } else if (ix >= (float)(w - 1)) { ix = (float)(w - 1); s.mx = 0.f; }
+    if (iy <= 0.f) { iy = 0.f; s.my = 0.f; } else if (iy >= (float)(h - 1)) { iy = (float)(h - 1); s.my = 0.f; }
+  }
+  const float fx = floorf(ix), fy = floorf(iy);
+  s.x0 = (int)fx; s.y0 = (int)fy; s.tx = ix - fx; s.ty = iy - fy;
+  return s;
+}
+
+__global__ void __launch_bounds__(256) grid_sample_fwd_kernel(const float* __restrict__ img, const float* __restrict__ grid,
+                                                              int n, int c, int h, int w, int oh, int ow, int border,
+                                                              float* __restrict__ out) {
+  const int64_t total = (int64_t)n * oh * ow;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((int64_t)oh * ow));
+    const float2 g = reinterpret_cast<const float2*>(grid)[i];
+    const Sample s = locate(g.x, g.y, h, w, border);
+    const int x1 = s.x0 + 1, y1 = s.y0 + 1;
+    const float w00 = (1.f - s.tx) * (1.f - s.ty), w01 = s.tx * (1.f - s.ty), w10 = (1.f - s.tx) * s.ty, w11 = s.tx * s.ty;
+    const bool vx0 = s.x0 >= 0 && s.x0 < w, vx1 = x1 >= 0 && x1 < w, vy0 = s.y0 >= 0 && s.y0 < h, vy1 = y1 >= 0 && y1 < h;
+    const int64_t pix = i - (int64_t)b * oh * ow;
+    for (int ch = 0; ch < c; ++ch) {
+      const float* p = img + ((int64_t)b * c + ch) * h * w;
+      float v = 0.f;
+      if (vy0 && vx0) v += p[(int64_t)s.y0 * w + s.x0] * w00;
+      if (vy0 && vx1) v += p[(int64_t)s.y0 * w + x1] * w01;
+      if (vy1 && vx0) v += p[(int64_t)y1 * w + s.x0] * w10;
+      if (vy1 && vx1) v += p[(int64_t)y1 * w + x1] * w11;
+      out[((int64_t)b * c + ch) * oh * ow + pix] = v;
+    }
+  }
+}
+
+// d_img (scatter-add over the 4 corners: fp32 atomics, as ATen's own CUDA backward; pre-zeroed by the caller) and
+// d_grid (one thread per output pixel, no atomics).  Either output may be NULL.
+__global__ void __launch_bounds__(256) grid_sample_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ img,
+                                                              const float* __restrict__ grid, int n, int c, int h, int w,
+                                                              int oh, int ow, int border, float* __restrict__ dimg,
+                                                              float* __restrict__ dgrid) {
+  const int64_t total = (int64_t)n * oh * ow;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int b = (int)(i / ((int64_t)oh * ow));
+    const float2 g = reinterpret_cast<const float2*>(grid)[i];
+    const Sample s = locate(g.x, g.y, h, w, border);
+    const int x1 = s.x0 + 1, y1 = s.y0 + 1;
+    const float w00 = (1.f - s.tx) * (1.f - s.ty), w01 = s.tx * (1.f - s.ty), w10 = (1.f - s.tx) * s.ty, w11 = s.tx * s.ty;
+    const bool vx0 = s.x0 >= 0 && s.x0 < w, vx1 = x1 >= 0 && x1 < w, vy0 = s.y0 >= 0 && s.y0 < h, vy1 = y1 >= 0 && y1 < h;
+    const int64_t pix = i - (int64_t)b * oh * ow;
+    float gix = 0.f, giy = 0.f;
+    for (int ch = 0; ch < c; ++ch) {
+      const float go = gout[((int64_t)b * c + ch) * oh * ow + pix];
+      const int64_t base = ((int64_t)b * c + ch) * h * w;
+      if (dimg) {
+        if (vy0 && vx0) atomicAdd(dimg + base + (int64_t)s.y0 * w + s.x0, go * w00);
+        if (vy0 && vx1) atomicAdd(dimg + base + (int64_t)s.y0 * w + x1, go * w01);
+        if (vy1 && vx0) atomicAdd(dimg + base + (int64_t)y1 * w + s.x0, go * w10);
+        if (vy1 && vx1) atomicAdd(dimg + base + (int64_t)y1 * w + x1, go * w11);
+      }
+      if (dgrid) {
+        const float* p = img + base;
+        const float v00 = (vy0 && vx0) ? p[(int64_t)s.y0 * w + s.x0] : 0.f, v01 = (vy0 && vx1) ? p[(int64_t)s.y0 * w + x1] : 0.f;
+        const float v10 = (vy1 && vx0) ? p[(int64_t)y1 * w + s.x0] : 0.f, v11 = (vy1 && vx1) ? p[(int64_t)y1 * w + x1] : 0.f;
+        gix += go * ((v01 - v00) * (1.f - s.ty) + (v11 - v10) * s.ty);
+        giy += go * ((v10 - v00) * (1.f - s.tx) + (v11 - v01) * s.tx);
+      }
+    }
+    if (dgrid) reinterpret_cast<float2*>(dgrid)[i] = make_float2(gix * s.mx, giy * s.my);
+  }
+}
+
+int blocks_for(int64_t total) {
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 32 * eg_sm_count()) blocks = 32 * eg_sm_count();
+  return blocks < 1 ? 1 : blocks;
+}
+
+}  // namespace
+
+extern "C" int eadgan_affine_grid_fwd(const float* theta, int n, int h, int w, float* grid, void* stream) {
+  EG_REQUIRE(theta && grid && n > 0 && h > 0 && w > 0, EADGAN_ERR_INVALID, "affine_grid_fwd: bad arguments");
+  affine_grid_fwd_kernel<<<blocks_for((int64_t)n * h * w), 256, 0, (cudaStream_t)stream>>>(theta, n, h, w, grid);
+  EG_LAUNCH_CHECK("affine_grid_fwd_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_affine_grid_bwd(const float* dgrid, int n, int h, int w, float* dtheta, void* stream) {
+  EG_REQUIRE(dgrid && dtheta && n > 0 && h > 0 && w > 0, EADGAN_ERR_INVALID, "affine_grid_bwd: bad arguments");
+  affine_grid_bwd_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(dgrid, h, w, dtheta);
+  EG_LAUNCH_CHECK("affine_grid_bwd_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_grid_sample_fwd(const float* img, const float* grid, int n, int c, int h, int w, int oh, int ow,
+                                      int padding_border, float* out, void* stream) {
+  EG_REQUIRE(img && grid && out && n > 0 && c > 0 && h > 0 && w > 0 && oh > 0 && ow > 0, EADGAN_ERR_INVALID,
+             "grid_sample_fwd: bad arguments");
+  grid_sample_fwd_kernel<<<blocks_for((int64_t)n * oh * ow), 256, 0, (cudaStream_t)stream>>>(img, grid, n, c, h, w, oh, ow,
+                                                                                          padding_border, out);
+  EG_LAUNCH_CHECK("grid_sample_fwd_kernel");
+  return 0;
+}
+
+extern "C" int eadgan_grid_sample_bwd(const float* gout, const float* img, const float* grid, int n, int c, int h, int w,
+                                      int oh, int ow, int padding_border, float* dimg_zeroed, float* dgrid, void* stream) {
+  EG_REQUIRE(gout && img && grid && (dimg_zeroed || dgrid) && n > 0 && c > 0 && h > 0 && w > 0 && oh > 0 && ow > 0,
+             EADGAN_ERR_INVALID, "grid_sample_bwd: bad arguments");
+  grid_sample_bwd_kernel<<<blocks_for((int64_t)n * oh * ow), 256, 0, (cudaStream_t)stream>>>(
+      gout, img, grid, n, c, h, w, oh, ow, padding_border, dimg_zeroed, dgrid);
+  EG_LAUNCH_CHECK("grid_sample_bwd_kernel");
+  return 0;
+}
+
 extern "C" int eadgan_relcode_dims(int mode, int* k_in, int* k_out) {
   EG_REQUIRE(mode >= 0 && mode <= 2 && k_in && k_out, EADGAN_ERR_INVALID, "relcode_dims: bad mode %d", mode);
   *k_in = mode == 0 ? 5 : (mode == 1 ? 4 : 7);

@@ -575,3 +575,69 @@ def stn_fwd(img, theta23, border=True):
     out = torch.empty_like(img)
     call("eadgan_stn_fwd", ptr(img), ptr(theta), n, c, h, w, 1 if border else 0, ptr(out), stream())
     return out
+
+
+# ---- F.affine_grid / F.grid_sample as differentiable operators (csrc/glue.cu) --------------------------------------------
+class _AffineGridFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, n, h, w):
+        grid = torch.empty((n, h, w, 2), device=theta.device, dtype=torch.float32)
+        call("eadgan_affine_grid_fwd", ptr(theta), n, h, w, ptr(grid), stream())
+        ctx.dims = (n, h, w)
+        return grid
+
+    @staticmethod
+    def backward(ctx, dgrid):
+        n, h, w = ctx.dims
+        dtheta = torch.empty((n, 2, 3), device=dgrid.device, dtype=torch.float32)
+        call("eadgan_affine_grid_bwd", ptr(dgrid.contiguous()), n, h, w, ptr(dtheta), stream())
+        return dtheta, None, None, None
+
+
+def affine_grid(theta, size, align_corners=None):
+    """F.affine_grid(theta [N,2,3], size (N,C,H,W), align_corners=False) -> [N,H,W,2]
+    (celebA/EAD-GAN_celebA.py:150, dSprites/rp.py:205)."""
+    if align_corners:
+        raise RuntimeError("eadgan_b200 affine_grid: align_corners=True is not used by the reference and unsupported")
+    if not (theta.is_cuda and theta.dtype == torch.float32 and theta.dim() == 3 and tuple(theta.shape[1:]) == (2, 3)):
+        raise RuntimeError("eadgan_b200 affine_grid: theta must be a CUDA fp32 [N, 2, 3] tensor (no CPU fallback)")
+    size = tuple(int(v) for v in size)
+    if len(size) != 4 or size[0] != theta.shape[0]:
+        raise RuntimeError("eadgan_b200 affine_grid: size must be (N, C, H, W) with N = theta.shape[0]")
+    return _AffineGridFn.apply(theta.contiguous(), size[0], size[2], size[3])
+
+
+class _GridSampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img, grid, border):
+        n, c, h, w = img.shape
+        oh, ow = grid.shape[1], grid.shape[2]
+        out = torch.empty((n, c, oh, ow), device=img.device, dtype=torch.float32)
+        call("eadgan_grid_sample_fwd", ptr(img), ptr(grid), n, c, h, w, oh, ow, int(border), ptr(out), stream())
+        ctx.save_for_backward(img, grid)
+        ctx.border = int(border)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        img, grid = ctx.saved_tensors
+        n, c, h, w = img.shape
+        oh, ow = grid.shape[1], grid.shape[2]
+        dimg = torch.zeros_like(img) if ctx.needs_input_grad[0] else None
+        dgrid = torch.empty_like(grid) if ctx.needs_input_grad[1] else None
+        if dimg is not None or dgrid is not None:
+            call("eadgan_grid_sample_bwd", ptr(gout.contiguous()), ptr(img), ptr(grid), n, c, h, w, oh, ow, ctx.border,
+                 ptr(dimg), ptr(dgrid), stream())
+        return dimg, dgrid, None
+
+
+def grid_sample(input, grid, mode="bilinear", padding_mode="zeros", align_corners=None):
+    """F.grid_sample(input [N,C,H,W], grid [N,Ho,Wo,2], 'bilinear', 'border' | 'zeros', align_corners=False)
+    (celebA/EAD-GAN_celebA.py:151, colored_dSprites/pxy_color.py:90) with both gradients."""
+    if mode != "bilinear" or padding_mode not in ("border", "zeros") or align_corners:
+        raise RuntimeError("eadgan_b200 grid_sample: only bilinear, padding_mode 'border' | 'zeros', align_corners=False")
+    if not (input.is_cuda and grid.is_cuda and input.dtype == torch.float32 and grid.dtype == torch.float32
+            and input.dim() == 4 and grid.dim() == 4 and grid.shape[0] == input.shape[0] and grid.shape[3] == 2):
+        raise RuntimeError("eadgan_b200 grid_sample: CUDA fp32 input [N,C,H,W] and grid [N,Ho,Wo,2] required "
+                           "(no CPU fallback)")
+    return _GridSampleFn.apply(input.contiguous(), grid.contiguous(), padding_mode == "border")

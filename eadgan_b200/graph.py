@@ -46,10 +46,6 @@ class GraphedStep:
         # packed-weight cache: a hit during capture would leave the pack kernel OUT of the graph (stale weights on
         # replay), and an entry filled during capture holds nothing until the first replay -> clear on both sides
         tc.invalidate_caches()
-        # halo-buffer pool and per-stream workspaces: start the capture with empty caches, so every buffer the
-        # captured kernels address is allocated from the graph's PRIVATE pool (kept alive by the graph), and empty them
-        # again afterwards, so that no eager call or later capture is handed -- or frees -- memory the graph uses
-        tc.clear_pool()
         # Capture on the SAME side stream the warm-up ran on.  AccumulateGrad nodes created during warm-up outlive it
         # and keep running on the stream they were created on; with torch's default (separate) capture stream their
         # kernels were pulled into the capture through an event while their allocations came from the REGULAR pool
@@ -62,9 +58,15 @@ class GraphedStep:
         finally:
             births, tc.capture_births = tc.capture_births, None
         for b in births:
-            b.zero_()        # see tc.alloc_padded: make the recorded zero fills real before the first replay
-        del births
-        tc.clear_pool()
+            b.zero_()        # see tc.alloc_padded: make the recorded zero fills real before anyone else reuses them
+        # The graph has baked in the addresses of every pooled halo buffer and per-stream workspace the step used --
+        # regular-pool memory that only module-level caches keep alive.  Hold strong references for the life of the
+        # graph: tc.clear_pool(), or a larger workspace replacing a cache entry, can then no longer free memory under
+        # the graph.  (The warm-up steps filled the pool, so capture creates almost no buffer: a buffer first created
+        # INSIDE a capture has its zero fill recorded and re-executed by every replay.)
+        from . import functional as Fn
+        self._keepalive = ([b for free in tc._pool.values() for b in free] + births + list(tc._ws_cache.values())
+                           + list(Fn._ws_cache.values()))
         tc.invalidate_caches()
         self.kernels_per_replay = int(_lib.lib().eadgan_kernel_launches() - k0)
         self._first = True

@@ -4,7 +4,7 @@ replacements, so the UNMODIFIED reference scripts run on the sm_100a kernels
 
 Patched names: torch.nn.{Sequential, Conv2d, ConvTranspose2d, Linear, BatchNorm2d, LeakyReLU,
 ReLU, Tanh, Sigmoid, Softmax, Upsample, BCELoss, MSELoss, CrossEntropyLoss},
-torch.nn.utils.spectral_norm, torch.nn.functional.{sigmoid, softmax},
+torch.nn.utils.spectral_norm, torch.nn.functional.{sigmoid, softmax, affine_grid, grid_sample},
 torch.optim.Adam.
 """
 from __future__ import annotations
@@ -48,6 +48,12 @@ def patch():
     _saved[("F", "softmax")] = TF.softmax
     TF.sigmoid = sigmoid
     TF.softmax = softmax
+    # transformation_2D.stn of every script: F.affine_grid + F.grid_sample, forward AND backward (dSprites/rp.py reaches
+    # the backward through its grad-tracked frozen Encoder_pxy)
+    _saved[("F", "affine_grid")] = TF.affine_grid
+    _saved[("F", "grid_sample")] = TF.grid_sample
+    TF.affine_grid = Fn.affine_grid
+    TF.grid_sample = Fn.grid_sample
     _saved[("optim", "Adam")] = torch.optim.Adam
     torch.optim.Adam = eoptim.Adam
 

@@ -359,6 +359,15 @@ int eadgan_zero_halo(void* xp, int n, int h, int w, int c, void* stream);
 /* ------------------------------------------------------------------------- */
 int eadgan_stn_fwd(const float* img, const float* theta, int n, int c, int h, int w, int padding_border,
                    float* out, void* stream);
+/* F.affine_grid / F.grid_sample (bilinear, align_corners = False, padding 'border' (1) | 'zeros' (0)) as separate
+ * differentiable operators, for the unmodified scripts (dSprites/rp.py:200-211,374-377,399-400 reach their backward).
+ * grid [n,oh,ow,2] fp32; grid_sample_bwd: dimg must be ZEROED by the caller (scatter-add), either output may be NULL. */
+int eadgan_affine_grid_fwd(const float* theta, int n, int h, int w, float* grid, void* stream);
+int eadgan_affine_grid_bwd(const float* dgrid, int n, int h, int w, float* dtheta, void* stream);
+int eadgan_grid_sample_fwd(const float* img, const float* grid, int n, int c, int h, int w, int oh, int ow,
+                           int padding_border, float* out, void* stream);
+int eadgan_grid_sample_bwd(const float* gout, const float* img, const float* grid, int n, int c, int h, int w, int oh,
+                           int ow, int padding_border, float* dimg_zeroed, float* dgrid, void* stream);
 int eadgan_relcode_dims(int mode, int* k_in, int* k_out);
 int eadgan_relcode_fwd(int mode, const float* real, long long real_stride, const float* trans,
                        long long trans_stride, int n, float* out, float* jac, void* stream);
