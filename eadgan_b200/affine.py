@@ -229,3 +229,14 @@ def pxy_relative_code(real_code, trans_code):
         rel = (trans_code[:, 3:] * 0.1 + 1) / (real_code[:, 3:] * 0.1 + 1)
         out = torch.cat((out, (rel - 1) / 0.1), dim=1)
     return out
+
+
+def inverse3x3(m):
+    """batched inverse of [B, 3, 3] matrices by the adjugate (rows of the inverse's transpose are cross products of
+    the rows) -- what the scripts' ``torch.inverse(get_matrix*(code))`` computes (dSprites/rp.py:376,
+    celebA/utils_rpqxy.py:92), without the host synchronisation torch.linalg's singularity check costs per call.
+    Differentiable through ordinary autograd."""
+    r0, r1, r2 = m[:, 0], m[:, 1], m[:, 2]
+    c0, c1, c2 = torch.cross(r1, r2, dim=1), torch.cross(r2, r0, dim=1), torch.cross(r0, r1, dim=1)
+    det = (r0 * c0).sum(dim=1, keepdim=True)
+    return torch.stack((c0 / det, c1 / det, c2 / det), dim=2)

@@ -103,6 +103,8 @@ def _plan(seq):
 
 
 _sn_streams = {}
+prefetch_enabled = True     # False: prefetch_spectral_norm is a no-op and every forward runs its own power iteration
+                            # (state snapshots taken BETWEEN phases then hold u / v exactly as far as the forwards got)
 
 
 def prefetch_spectral_norm(seq, count=1):
@@ -114,7 +116,7 @@ def prefetch_spectral_norm(seq, count=1):
     backward pass) instead of sitting, 4 small launches per layer, on the critical path in front of every conv
     stack.  Results are queued per module in forward order; ``try_run`` consumes them (and waits on the side
     stream's event) instead of calling the hooks.  Same arithmetic, same order of u / v updates."""
-    if precision() != "bf16":
+    if precision() != "bf16" or not prefetch_enabled:
         return
     stages = _plan(seq)
     if stages is None:

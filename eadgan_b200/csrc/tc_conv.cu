@@ -448,6 +448,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         const int m_grp = (r / P.parities) * CG + rank;   // this CTA's group of MT consecutive 128-row tiles
         const int py = parity >> 1, px = parity & 1;
         const int n0 = n_tile * BLOCK_N + rank * (BLOCK_N / CG);      // first B row this CTA stages
+        const int b_row = (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0;
+        // Everything that needs an integer division is computed ONCE PER TILE: this single thread issues every load
+        // of the CTA, and with divisions inside the k loop it was the instruction-bound stage of the whole pipeline
+        // (ncu r02a: the producer never waited for a free slot while the MMA warp waited for data a quarter of the time)
+        int b0[MT], y0[MT];
+#pragma unroll
+        for (int h = 0; h < MT; ++h) {
+          const int m_tile = m_grp * MT + h;
+          if (P.mode == MODE_GEMM || P.mode == MODE_DENSE_GATHER) { b0[h] = m_tile * BLOCK_M; y0[h] = 0; }
+          else { b0[h] = (m_tile / P.tiles_y) * P.Tb; y0[h] = (m_tile % P.tiles_y) * P.Th; }
+        }
+        // k block -> (tap t, 64-channel block qi); dense gather: the K range is split over the "parity" index (split-K)
+        const int kb0 = P.mode == MODE_DENSE_GATHER ? parity * P.nkb : 0;
+        int qi = kb0 % P.qblocks, t = kb0 / P.qblocks;
+#pragma unroll 1
         for (int kb = 0; kb < P.nkb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = tiles + stage * C::STAGE_BYTES;
@@ -459,38 +474,35 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           } else {
             mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           }
-          // dense gather: the K range (16 taps x channels) is split over the "parity" index (split-K)
-          const int kbg = P.mode == MODE_DENSE_GATHER ? parity * P.nkb + kb : kb;
-          const int qi = kbg % P.qblocks, t = kbg / P.qblocks;
+          const int kcol = qi * BLOCK_K;
+          int b_col = (kb0 + kb) * BLOCK_K;
+          if (P.mode == MODE_GEMM) {
 #pragma unroll
-          for (int h = 0; h < MT; ++h) {
-            const int m_tile = m_grp * MT + h;
-            uint8_t* sah = sa + h * A_BYTES;
-            if (P.mode == MODE_GEMM) {
-              tma_load_2d<CG>(sah, &map_a, fb, kb * BLOCK_K, m_tile * BLOCK_M);
-            } else if (P.mode == MODE_DENSE_GATHER) {
-              // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]  (t = tap)
-              tma_load_4d<CG>(sah, &map_a, fb, qi * BLOCK_K, 1 + (t & 3), 1 + (t >> 2), m_tile * BLOCK_M);
-            } else {
-              const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
-              if (P.mode == MODE_FPROP && P.thin) {
-                // R[n][oy][X][ky][4]: the 4x4x4 patch of output (oy, ox) is the 64 contiguous elements at X = 2 ox
-                tma_load_4d<CG>(sah, &map_a, fb, 0, 0, y0, b0);
-              } else if (P.mode == MODE_FPROP) {
-                const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-                tma_load_5d<CG>(sah, &map_a, fb, qi * BLOCK_K, bt, dy, y0 + at, b0);
-              } else {  // t = ty*2+tx
-                const int ty = t >> 1, tx = t & 1;
-                const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
-                const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
-                tma_load_4d<CG>(sah, &map_a, fb, qi * BLOCK_K, 1 + dx, y0 + 1 + dy, b0);
-              }
-            }
+            for (int h = 0; h < MT; ++h) tma_load_2d<CG>(sa + h * A_BYTES, &map_a, fb, kb * BLOCK_K, b0[h]);
+          } else if (P.mode == MODE_DENSE_GATHER) {
+            // A[b][(tap, c)] = Y[b][1+ky][1+kx][c]: box [64 ch] x 1 x 1 x [128 images]  (t = tap)
+#pragma unroll
+            for (int h = 0; h < MT; ++h) tma_load_4d<CG>(sa + h * A_BYTES, &map_a, fb, kcol, 1 + (t & 3), 1 + (t >> 2), b0[h]);
+          } else if (P.mode == MODE_FPROP && P.thin) {
+            // R[n][oy][X][ky][4]: the 4x4x4 patch of output (oy, ox) is the 64 contiguous elements at X = 2 ox
+#pragma unroll
+            for (int h = 0; h < MT; ++h) tma_load_4d<CG>(sa + h * A_BYTES, &map_a, fb, 0, 0, y0[h], b0[h]);
+          } else if (P.mode == MODE_FPROP) {
+            const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
+#pragma unroll
+            for (int h = 0; h < MT; ++h) tma_load_5d<CG>(sa + h * A_BYTES, &map_a, fb, kcol, bt, dy, y0[h] + at, b0[h]);
+          } else {  // dgrad: t = ty*2+tx
+            const int ty = t >> 1, tx = t & 1;
+            const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+            const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+#pragma unroll
+            for (int h = 0; h < MT; ++h) tma_load_4d<CG>(sa + h * A_BYTES, &map_a, fb, kcol, 1 + dx, y0[h] + 1 + dy, b0[h]);
+            // tap t's weights start at column t * K_ch (= kb * 64 whenever K_ch is a multiple of 64; for K_ch = 32 the
+            // box also covers 32 columns of the next tap, multiplied by the zero-filled half of A)
+            b_col = t * P.K_ch + kcol;
           }
-          // dgrad: tap t's weights start at column t * K_ch (= kb * 64 whenever K_ch is a multiple of 64; for
-          // K_ch = 32 the box also covers 32 columns of the next tap, multiplied by the zero-filled half of A)
-          tma_load_2d<CG>(sb, &map_b, fb, P.mode == MODE_DGRAD ? t * P.K_ch + qi * BLOCK_K : kbg * BLOCK_K,
-                      (P.mode == MODE_DGRAD ? parity * P.N_total : 0) + n0);
+          tma_load_2d<CG>(sb, &map_b, fb, b_col, b_row);
+          if (++qi == P.qblocks) { qi = 0; ++t; }
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -816,6 +828,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
         const int nb0 = (kk_tile * CG + rank) * C::NB;               // ... and its first 64-column patch block
         const int step0 = split * P.steps_per_split;
         const int step1 = min(P.steps_total, step0 + P.steps_per_split);
+        // per-item constants (no integer division inside the step loop: this one thread issues every load of the CTA)
+        int qis[C::NB], taps[C::NB];
+#pragma unroll
+        for (int i = 0; i < C::NB; ++i) { qis[i] = ((nb0 + i) % P.qblocks) * 64; taps[i] = (nb0 + i) / P.qblocks; }
+        int ty_i = P.dense ? 0 : step0 % P.tiles_y, tb_i = P.dense ? 0 : step0 / P.tiles_y;
+#pragma unroll 1
         for (int st = step0; st < step1; ++st) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -832,14 +850,12 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             for (int h = 0; h < 2; ++h)
               tma_load_2d<CG>(sa + h * 8192, &map_dy, fb, ko0 + h * 64, st * 64);
 #pragma unroll
-            for (int i = 0; i < C::NB; ++i) {
-              const int nb = nb0 + i;
-              const int qi = nb % P.qblocks, tap = nb / P.qblocks;  // tap = ky*4+kx
-              tma_load_4d<CG>(sb + i * 8192, &map_x, fb, qi * 64, 1 + (tap & 3), 1 + (tap >> 2), st * 64);
-            }
+            for (int i = 0; i < C::NB; ++i)   // tap = ky*4+kx
+              tma_load_4d<CG>(sb + i * 8192, &map_x, fb, qis[i], 1 + (taps[i] & 3), 1 + (taps[i] >> 2), st * 64);
           } else {
-            const int b0 = (st / P.tiles_y) * P.Tb;
-            const int y0 = (st % P.tiles_y) * P.Th;
+            const int b0 = tb_i * P.Tb;
+            const int y0 = ty_i * P.Th;
+            if (++ty_i == P.tiles_y) { ty_i = 0; ++tb_i; }
 #pragma unroll
             for (int h = 0; h < 2; ++h)
               tma_load_4d<CG>(sa + h * 8192, &map_dy, fb, ko0 + h * 64, 1, y0 + 1, b0);
@@ -848,10 +864,8 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_constan
             } else {
 #pragma unroll
               for (int i = 0; i < C::NB; ++i) {
-                const int nb = nb0 + i;  // 64-wide column block index
-                const int qi = nb % P.qblocks, t = nb / P.qblocks;
-                const int dy = t & 1, bt = (t >> 1) & 1, at = t >> 2;
-                tma_load_5d<CG>(sb + i * 8192, &map_x, fb, qi * 64, bt, dy, y0 + at, b0);
+                const int t = taps[i];
+                tma_load_5d<CG>(sb + i * 8192, &map_x, fb, qis[i], (t >> 1) & 1, t & 1, y0 + (t >> 2), b0);
               }
             }
           }
@@ -1191,6 +1205,7 @@ int dispatch_conv(const TileCfg& t, const CUtensorMap& ma, const CUtensorMap& mb
                   int parities, cudaStream_t st) {
   const int bn = t.bn, mt = t.mt, per = t.mt * t.cg;
   P.m_tiles = (m_tiles + per - 1) / per; P.n_tiles = n_total / bn; P.parities = parities;
+  if (P.qblocks <= 0) P.qblocks = 1;   // plain GEMMs: the producer's (tap, channel block) counters are unused
   P.bias_len = P.bias ? (P.dense_C > 0 ? P.dense_C : P.n_store) : 0;
   EG_REQUIRE(P.bias_len <= STAT_MAX_CH, EADGAN_ERR_UNSUPPORTED, "tc conv: fused bias supports at most %d channels (got %d)",
              STAT_MAX_CH, P.bias_len);

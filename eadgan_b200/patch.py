@@ -5,7 +5,7 @@ replacements, so the UNMODIFIED reference scripts run on the sm_100a kernels
 Patched names: torch.nn.{Sequential, Conv2d, ConvTranspose2d, Linear, BatchNorm2d, LeakyReLU,
 ReLU, Tanh, Sigmoid, Softmax, Upsample, BCELoss, MSELoss, CrossEntropyLoss},
 torch.nn.utils.spectral_norm, torch.nn.functional.{sigmoid, softmax, affine_grid, grid_sample},
-torch.optim.Adam.
+torch.optim.Adam, torch.inverse (batched 3x3 on CUDA: closed form, no host synchronisation).
 """
 from __future__ import annotations
 
@@ -36,6 +36,15 @@ def softmax(input, dim=None, _stacklevel=3, dtype=None):
     return Fn.softmax(input)
 
 
+def inverse(input, *, out=None):
+    """torch.inverse drop-in: batched CUDA [B, 3, 3] matrices (every use in the reference: the 3x3 affine matrices of
+    utils_*.py) go through the closed-form adjugate on the device; anything else through stock torch."""
+    if out is None and torch.is_tensor(input) and input.is_cuda and input.dim() == 3 and tuple(input.shape[1:]) == (3, 3):
+        from . import affine
+        return affine.inverse3x3(input)
+    return _saved[("torch", "inverse")](input) if out is None else _saved[("torch", "inverse")](input, out=out)
+
+
 def patch():
     if _saved:
         return
@@ -56,6 +65,8 @@ def patch():
     TF.grid_sample = Fn.grid_sample
     _saved[("optim", "Adam")] = torch.optim.Adam
     torch.optim.Adam = eoptim.Adam
+    _saved[("torch", "inverse")] = torch.inverse
+    torch.inverse = inverse
 
 
 def unpatch():
@@ -68,4 +79,6 @@ def unpatch():
             setattr(TF, n, v)
         elif where == "optim":
             torch.optim.Adam = v
+        elif where == "torch":
+            setattr(torch, n, v)
     _saved.clear()

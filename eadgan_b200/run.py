@@ -2,7 +2,10 @@
 
 Patches torch (eadgan_b200.patch) and runs the unmodified reference training script
 with ``runpy`` from the current working directory, which must hold whatever dataset /
-artefact files the script opens.
+artefact files the script opens.  The script's ``utils_*.py`` helper
+module is shadowed by its device-side restatement (eadgan_b200/shadow; EADGAN_NO_SHADOW=1 turns
+that off).  Under ``torchrun`` every rank runs the script on its own data shard: optimisers
+all-reduce their gradients and train-mode BatchNorm layers synchronise their statistics.
 """
 import os
 import runpy
@@ -20,6 +23,11 @@ def main():
     apply_patch()
     sys.argv = [script] + sys.argv[2:]
     sys.path.insert(0, os.path.dirname(script))
+    from .shadow import shadow_dir_for
+    shadow = None if os.environ.get("EADGAN_NO_SHADOW") == "1" else shadow_dir_for(script)
+    if shadow is not None:
+        # ``from utils_x import *`` in the script now finds the device-side restatements of the affine glue first
+        sys.path.insert(0, shadow)
     runpy.run_path(script, run_name="__main__")
 
 

@@ -5,6 +5,8 @@ import pytest
 import torch
 import torch.nn.functional as TF
 
+from conftest import rel_err
+
 pytestmark = pytest.mark.gpu
 
 

@@ -25,8 +25,18 @@ def dp_parity(B_local, dev, seed=0):
     lr * sign(g) noise of one phase does not leak into the next: all three phases are compared from common weights).
     Compared: the three losses (mean over ranks), every all-reduced + averaged gradient of every phase, BatchNorm
     running statistics after the step."""
-    from eadgan_b200 import synthetic
+    from eadgan_b200 import chain, synthetic
     dp = parallel.get()
+    # the phases restart from state snapshots taken between them: run every spectral-norm power iteration in line, so
+    # that a snapshot holds u / v exactly as far as the forwards got (a prefetch runs up to three iterations ahead)
+    saved_prefetch, chain.prefetch_enabled = chain.prefetch_enabled, False
+    try:
+        return _dp_parity(B_local, dev, seed, dp, synthetic)
+    finally:
+        chain.prefetch_enabled = saved_prefetch
+
+
+def _dp_parity(B_local, dev, seed, dp, synthetic):
     world, rank = dp.world_size, dp.rank
     Bg = B_local * world
     imgs = synthetic.celeba_images(Bg, seed)
