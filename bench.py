@@ -365,6 +365,12 @@ def _main():
         barrier()
 
     eager_step, sampled, host = build_step(args.config, dev, rank, B)
+    ablate = os.environ.get("EADGAN_DP_ABLATE", "")     # experiments: which exchange costs what (profiles/r02*_dp_ablation)
+    if world > 1 and "grads" in ablate:
+        parallel.detach(*eager_step.optimizers())       # no gradient all-reduce (replicas diverge: timing only)
+    if world > 1 and "syncbn" in ablate:
+        from eadgan_b200 import functional as _Fn
+        _Fn.set_allreduce(None, 1)                       # BatchNorm statistics stay local (timing only)
     R = len(host)
     resident = [h.to(dev) for h in host]
     h2d_bytes = host[0].numel() * host[0].element_size()

@@ -259,6 +259,7 @@ struct TcParams {
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
   int thin;            // fprop on a <= 4-channel image: ONE 64-wide k block, A boxes from the row-expanded buffer
   int bias_len;        // number of bias entries (n_store, or dense_C for the scatter GEMM)
+  int dbg;             // experiments only (EADGAN_TC_DBG): bit 0 skip the global stores, bit 1 skip the staging tile too
   const float* sigma;  // spectral-norm sigma (device scalar) or NULL: accumulators are multiplied by 1/sigma, so the
                        // packed bf16 operand can be the UN-normalised weight_orig (cached across forwards)
 };
@@ -687,6 +688,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
                   if (j < n_left) op[(int64_t)j * ch_stride] = v[j];
               }
             } else {
+              // (measured, r02o: exchanging 16-byte pieces inside lane quads so that every store instruction writes
+              // eight 64-byte runs instead of 32 scattered 16-byte pieces made the step 1 ms SLOWER -- this epilogue
+              // is bound by instruction issue and latency, not by the number of lines its stores touch)
               __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(P.out) + ri.out_off + c0;
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -744,6 +748,284 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if constexpr (CG == 2) cluster_sync();   // the leader's MMAs read the peer's shared memory: nobody leaves early
   if (warp == 1) tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------
+// CHANNEL-MAJOR kernel ("transposed" GEMM) for layers with 128 output channels: the c = 128 dgrad below, and the thin
+// image-layer fprop Conv2d(3,128) (celebA/EAD-GAN_celebA.py:110; one 64-wide k block per tile, purely epilogue- /
+// HBM-bound: the per-lane-scalar epilogue below needs a third of the instructions of the pixel-major one).
+// TRANSPOSED dgrad for layers with 128 output channels per parity (ConvTranspose2d(256,128) forward / Conv2d(128,256)
+// input gradient: the dominant kernel of the CelebA step, celebA/EAD-GAN_celebA.py:86,113).
+//
+// With N = c = 128 the pixel-major formulation is stuck with 128-wide UMMAs, whose operand reads alone need the full
+// 128 B/clk of shared-memory bandwidth, on top of the TMA writes of the same data (ncu r02a: 45 % tensor-pipe, the
+// pipeline waits on shared memory, not on L2 or DRAM).  Here the SAME staged tiles are multiplied the other way round:
+//     D^T[channel][pixel] = Wd[128 channels][K] . X[256 pixels][K]^T        (M = 128, N = 256, K = 4 k per parity)
+// i.e. the packed weight tile is the A operand and the two 128-pixel tiles are ONE 256-row B operand: half as many,
+// twice as wide UMMAs (96 instead of 128 B/clk of operand reads), nothing else changes up to the accumulator.
+// In tensor memory a lane is now an output CHANNEL and a column a pixel, which makes the epilogue simpler: bias and
+// BatchNorm statistics are per-lane scalars (plain register accumulation, no cross-lane reduction), and for a given
+// pixel the 32 lanes of a warp hold 32 consecutive channels = one 64-byte run of the NHWC tensors, so the fused
+// activation-backward mask is read, and the result written, as full 32-byte sectors.
+// ------------------------------------------------------------------------------------
+struct DgTCfg {
+  static constexpr int STAGE_BYTES = 3 * A_BYTES;                 // two pixel tiles + one weight tile, 48 KB
+  static constexpr int STAGES = 4;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 2048 /* staging */ + 2 * 128 * 2 * 8 /* stats */;
+};
+
+__global__ void __launch_bounds__(320, 1)
+tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams P) {
+  using C = DgTCfg;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + C::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + C::STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile = (pixel-tile pair * parities + parity) * n_tiles + channel block; P.m_tiles counts PAIRS of 128-pixel tiles
+  const int total_tiles = P.parities * P.m_tiles * P.n_tiles;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
+        const int parity = r % P.parities, m_pair = r / P.parities;
+        const int py = parity >> 1, px = parity & 1;
+        int b0[2], y0[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int m_tile = m_pair * 2 + h;
+          b0[h] = (m_tile / P.tiles_y) * P.Tb; y0[h] = (m_tile % P.tiles_y) * P.Th;
+        }
+        const int w_row = parity * P.N_total + n_tile * 128;
+        int qi = 0, t = 0;
+#pragma unroll 1
+        for (int kb = 0; kb < P.nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sx = smem + stage * C::STAGE_BYTES;
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (P.thin) {   // thin fprop: the whole 4x4x(4) patch of an output pixel is ONE 64-element box row (K = 64)
+#pragma unroll
+            for (int h = 0; h < 2; ++h) tma_load_4d<1>(sx + h * A_BYTES, &map_x, fb, 0, 0, y0[h], b0[h]);
+            tma_load_2d<1>(sx + 2 * A_BYTES, &map_w, fb, 0, n_tile * 128);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          const int ty = t >> 1, tx = t & 1;
+          const int dy = py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0);
+          const int dx = px == 0 ? (tx == 0 ? 0 : -1) : (tx == 0 ? 1 : 0);
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+            tma_load_4d<1>(sx + h * A_BYTES, &map_x, fb, qi * BLOCK_K, 1 + dx, y0[h] + 1 + dy, b0[h]);
+          tma_load_2d<1>(sx + 2 * A_BYTES, &map_w, fb, t * P.K_ch + qi * BLOCK_K, w_row);
+          if (++qi == P.qblocks) { qi = 0; ++t; }
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = make_idesc(128, 256, 0, 0);
+    int stage = 0; uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tmem_empty_bar[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(buf * 256);
+      for (int kb = 0; kb < P.nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sx = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sw = sx + 2 * A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k)   // A = weights (128 channel rows), B = pixels (256 rows, two tiles back to back)
+            umma_bf16(d_tmem, make_desc(sw + k * 32, 16, 1024), make_desc(sx + k * 32, 16, 1024), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[stage]);
+          if (kb == P.nkb - 1) umma_commit(&tmem_full_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue: lane = output channel, column = pixel.  Warp (quad, h): channels quad*32.., pixel tile h =====
+    // Global traffic goes through a per-warp 2 KB staging tile [32 pixels][32 channels] bf16: the fused mask is read,
+    // and the result written, with 16-byte accesses (lane -> pixel lane/4 + 8 i, channel octet lane%4: every
+    // instruction covers eight 64-byte runs), while the per-channel view (lane = channel) uses conflict-free 2-byte
+    // shared-memory accesses.
+    const int quad = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
+    const int lTw = 31 - __clz(P.Tw), lTh = 31 - __clz(P.Th);
+    const int64_t row_stride = (int64_t)(P.OW + 2) * P.N_total, img_stride = (int64_t)(P.OH + 2) * row_stride;
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out);
+    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + (warp - 2) * 2048;
+    double* stat_s = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + 256 + 8 * 2048);   // [2 h][128][2]
+    const int et = threadIdx.x - 64;
+    float s1 = 0.f, s2 = 0.f;      // running per-channel statistics of this lane's channel (fp32 per CTA, fp64 across)
+    int cur_blk = -1;
+    auto flush = [&]() {           // all 8 epilogue warps: fold the two pixel-tile halves, one fp64 atomic per channel
+      stat_s[(h * 128 + quad * 32 + lane) * 2 + 0] = (double)s1;
+      stat_s[(h * 128 + quad * 32 + lane) * 2 + 1] = (double)s2;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (et < 128 && cur_blk >= 0) {
+        const int gch = cur_blk * 128 + et;
+        if (gch < P.stat_channels) {
+          atomicAdd(&P.stats[gch], stat_s[et * 2] + stat_s[(128 + et) * 2]);
+          if (P.want_stats == 1) atomicAdd(&P.stats[P.stat_channels + gch], stat_s[et * 2 + 1] + stat_s[(128 + et) * 2 + 1]);
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      s1 = 0.f; s2 = 0.f;
+    };
+    const int pl = lane >> 2, oct = lane & 3;          // 16-byte view: pixel pl + 8 i of the chunk, channel octet oct
+    const int up = P.mode == MODE_DGRAD ? 2 : 1;       // dgrad writes every second pixel of the big map (one parity), fprop all
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
+      const int parity = r % P.parities, m_tile = (r / P.parities) * 2 + h;
+      const int py = parity >> 1, px = parity & 1;
+      const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
+      if (P.want_stats && n_tile != cur_blk) {         // tile -> channel block is the same for every warp of the CTA
+        if (cur_blk >= 0) flush();
+        cur_blk = n_tile;
+      }
+      const int ch = n_tile * 128 + quad * 32 + lane;
+      const float bias = P.bias ? __ldg(&P.bias[ch]) : 0.f;
+      // columns are ordered (image, row, x): the valid ones (image < n) are a prefix
+      int nvalid = (P.n - b0) << (lTw + lTh);
+      nvalid = nvalid < 0 ? 0 : (nvalid > 128 ? 128 : nvalid);
+      auto pix_off = [&](int col) -> int64_t {         // element offset of (pixel of column `col`, first channel of this warp)
+        const int xl = col & (P.Tw - 1), yl = (col >> lTw) & (P.Th - 1), bl = col >> (lTw + lTh);
+        return (int64_t)(b0 + bl) * img_stride + (int64_t)(up * (y0 + yl) + py + 1) * row_stride +
+               (int64_t)(up * xl + px + 1) * P.N_total + n_tile * 128 + quad * 32 + oct * 8;
+      };
+      // the fused mask is software-pipelined one chunk ahead: its loads are in flight while the accumulator of the
+      // current chunk is read and processed (the first chunk's while this warp still waits for the MMAs)
+      uint4 mreg[4];
+      auto load_mask = [&](int cn) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          mreg[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (cn + pl + 8 * i < nvalid) mreg[i] = __ldg(reinterpret_cast<const uint4*>(P.mask + pix_off(cn + pl + 8 * i)));
+        }
+      };
+      if (P.mask_mode) load_mask(0);
+      const int buf = it & 1;
+      mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * 256 + h * 128) + ((uint32_t)(quad * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        int64_t goff[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) goff[i] = pix_off(c0 + pl + 8 * i);
+        if (P.mask_mode) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (pl + 8 * i) * 64 + oct * 16) = mreg[i];
+          if (c0 + 32 < 128) load_mask(c0 + 32);
+        }
+        float v[32];
+        tmem_ld32(acc + (uint32_t)c0, v);
+        if (c0 + 32 >= 128) {   // this warp's columns are all in registers: hand the accumulator back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+        }
+        __syncwarp();
+        // every mode switch is uniform for the launch: decided ONCE per chunk, outside the element loops
+        const bool all_valid = c0 + 32 <= nvalid;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_sigma, bias);
+        if (P.want_stats == 1) {
+          if (all_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < nvalid) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+          }
+        }
+        if (P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU) {
+          const float sl = P.act == EADGAN_ACT_RELU ? 0.f : P.slope;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+        } else if (P.act == EADGAN_ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+        } else if (P.act == EADGAN_ACT_SIGMOID) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+        }
+        if (P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU) {
+          const float sl = P.mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {   // saved OUTPUT y > 0 <=> pre-activation > 0: sign / zero test on the raw bf16 bits
+            const uint32_t mb = *reinterpret_cast<const uint16_t*>(stg + j * 64 + lane * 2);
+            if ((mb & 0x8000u) != 0 || (mb & 0x7fffu) == 0) v[j] *= sl;
+          }
+        } else if (P.mask_mode) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float m = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + j * 64 + lane * 2));
+            v[j] *= eg_act_grad(m, P.mask_mode, P.slope);
+          }
+        }
+        if (P.want_stats == 2) {
+          if (all_valid) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) s1 += v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (c0 + j < nvalid) s1 += v[j];
+          }
+        }
+        __syncwarp();           // every lane has read its mask column: the staging tile can take the result
+        if (!(P.dbg & 2)) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) = __float2bfloat16_rn(v[j]);
+        } else if (v[3] == 123.456f) out[0] = __float2bfloat16_rn(v[5]);
+        __syncwarp();
+        if (!(P.dbg & 1)) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c0 + pl + 8 * i < nvalid)
+              *reinterpret_cast<uint4*>(out + goff[i]) = *reinterpret_cast<const uint4*>(stg + (pl + 8 * i) * 64 + oct * 16);
+        }
+        __syncwarp();           // ... before the next chunk overwrites the tile
+      }
+    }
+    if (P.want_stats) flush();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------
@@ -1139,6 +1421,18 @@ int opt_in_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
   return 0;
 }
 
+int launch_channel_major(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P, cudaStream_t st) {
+  static std::atomic<uint64_t> opted{0};
+  if (int e = opt_in_smem(tc_dgradT_kernel, DgTCfg::SMEM, opted)) return e;
+  const int total = P.parities * P.m_tiles * P.n_tiles;
+  const int units = eg_tc_units();
+  const int waves = (total + units - 1) / units;
+  const int grid = (total + waves - 1) / waves;
+  tc_dgradT_kernel<<<grid, 320, DgTCfg::SMEM, st>>>(mx, mw, P);
+  EG_LAUNCH_CHECK("tc_dgradT_kernel");
+  return 0;
+}
+
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
 
 // tile of `pixels` positions of a p x q grid: Tw = q, Th rows, Tb images
@@ -1158,7 +1452,7 @@ int launch_conv(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& P,
   if (int e = opt_in_smem(tc_conv_kernel<BN, MT, CG>, Cfg<BN, MT, CG>::SMEM, opted)) return e;
   // persistent grid: every CTA (CTA pair) runs the same number of tiles (+-1), at most one CTA per SM
   const int total = P.parities * P.m_tiles * P.n_tiles;
-  int units = eg_sm_count() / CG;
+  int units = eg_tc_units() / CG;
   if (const char* e = getenv("EADGAN_TC_UNITS")) { if (atoi(e) > 0 && atoi(e) < units) units = atoi(e); }   // experiments
   const int waves = (total + units - 1) / units;
   const int grid = ((total + waves - 1) / waves) * CG;
@@ -1318,6 +1612,28 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
   const TileCfg tcfg = pick_cfg(d->c, m_tiles, 4, true);
   const int bn = tcfg.bn;
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: c=%d must be a multiple of 32", d->c);
+  // 128-channel outputs with a long pixel dimension: the transposed kernel (see tc_dgradT_kernel)
+  bool transposed = d->c == 128 && d->k % 64 == 0 && !d->out_f32_nchw && (d->c_real <= 0 || d->c_real == d->c);
+  bool enough = (int64_t)m_tiles * 4 >= 8 * eg_sm_count();
+  if (const char* e = getenv("EADGAN_TC_DGRADT")) { if (atoi(e) == 0) transposed = false; else if (atoi(e) == 2) enough = true; }
+  transposed = transposed && enough;
+  if (transposed) {
+    TcParams P{};
+    P.mode = MODE_DGRAD; P.n = d->n; P.p = p; P.q = q;
+    EG_REQUIRE(pick_tile(p, q, 128, &P.Tw, &P.Th, &P.Tb) == 0, EADGAN_ERR_UNSUPPORTED, "tc_dgrad: bad small map");
+    P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = d->k / 64; P.nkb = 4 * P.qblocks;
+    P.act = d->act; P.slope = d->slope; P.want_stats = d->want_stats; P.mask_mode = d->mask_mode;
+    P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx; P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
+    P.sigma = sigma; P.n_store = d->c; P.stat_channels = d->c;
+    P.m_tiles = (m_tiles + 1) / 2; P.n_tiles = d->c / 128; P.parities = 4;
+    if (const char* e = getenv("EADGAN_TC_DBG")) P.dbg = atoi(e);
+    EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_dgrad: mask_mode without mask");
+    EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_dgrad: want_stats without stats");
+    CUtensorMap mx, mw;
+    if (int e = map_small(&mx, dy_pad, d->n, d->k, p, q, P.Tw, P.Th, P.Tb)) return e;
+    if (int e = map_matrix(&mw, w_packed, (uint64_t)4 * d->c, (uint64_t)4 * d->k, 128)) return e;
+    return launch_channel_major(mx, mw, P, (cudaStream_t)stream);
+  }
   P.tiles_y = p / P.Th; P.N_total = d->c; P.K_ch = d->k; P.qblocks = (d->k + 63) / 64; P.nkb = 4 * P.qblocks;
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx;
@@ -1355,7 +1671,7 @@ int wgrad_plan(const eadgan_tc_desc* d, WgParams* P, int* bn, int* splits, int* 
   // split of the pixel reduction: one CTA per (tile, split) and one CTA per SM at a time, so the kernel runs in
   // waves of sm_count CTAs.  Pick the split count minimising  waves * steps_per_split  (tensor time, a 64-pixel
   // step of a 128 x bn tile is bn*2 clocks) plus the fp32 partial-sum traffic (written once, read once).
-  const int sms = eg_sm_count() / *cg;   // concurrently running CTAs (CTA pairs)
+  const int sms = eg_tc_units() / *cg;   // concurrently running CTAs (CTA pairs)
   const int max_s = (P->steps_total + 7) / 8;
   const int k_pad = ((d->k + 127) / 128) * 128;
   double best = 1e300;
@@ -1383,7 +1699,7 @@ int launch_wgrad(const CUtensorMap& mdy, const CUtensorMap& mx, const WgParams& 
   WgParams Q = P;
   Q.kk_tiles = (int)grid.x; Q.ko_tiles = (int)grid.y; Q.splits = (int)grid.z;
   const int total = Q.kk_tiles * Q.ko_tiles * Q.splits;
-  const int units = eg_sm_count() / CG;
+  const int units = eg_tc_units() / CG;
   const int waves = (total + units - 1) / units;
   const int ctas = ((total + waves - 1) / waves) * CG;
   cudaLaunchConfig_t cfg{};
@@ -1879,6 +2195,11 @@ extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, 
   EG_REQUIRE(bn > 0, EADGAN_ERR_UNSUPPORTED, "tc_thin_fprop: k=%d must be a multiple of 32", d->k);
   const TileCfg tcfg = pick_cfg(d->k, m_tiles, 1, false, bn);
   P.tiles_y = p / P.Th; P.N_total = d->k; P.K_ch = 4; P.qblocks = 1; P.nkb = 1;
+  bool channel_major = d->k % 128 == 0 && !d->out_f32_nchw && (int64_t)m_tiles * (d->k / 128) >= 8 * eg_sm_count();
+  if (const char* e = getenv("EADGAN_TC_DGRADT")) {
+    if (atoi(e) == 0) channel_major = false;
+    else if (atoi(e) == 2) channel_major = d->k % 128 == 0 && !d->out_f32_nchw;
+  }
   P.act = d->act; P.slope = d->slope; P.out_f32_nchw = d->out_f32_nchw; P.want_stats = d->want_stats;
   P.mask_mode = d->mask_mode; P.OH = p; P.OW = q; P.bias = bias; P.out = y;
   P.mask = (const __nv_bfloat16*)mask; P.stats = stats; P.n_store = d->k; P.stat_channels = d->k; P.sigma = sigma;
@@ -1886,6 +2207,11 @@ extern "C" int eadgan_tc_thin_fprop(const eadgan_tc_desc* d, const void* r_buf, 
   EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_thin_fprop: want_stats without stats");
   CUtensorMap ma, mb;
   if (int e = map_thin(&ma, r_buf, d->n, d->h, d->w, P.Tw, P.Th, P.Tb)) return e;
+  if (channel_major) {   // tc_dgradT_kernel: 128 channels x 256 pixels per tile
+    P.m_tiles = (m_tiles + 1) / 2; P.n_tiles = d->k / 128; P.parities = 1;
+    if (int e = map_matrix(&mb, w_packed, d->k, 64, 128)) return e;
+    return launch_channel_major(ma, mb, P, (cudaStream_t)stream);
+  }
   if (int e = map_matrix(&mb, w_packed, d->k, 64, bn)) return e;
   return dispatch_conv(tcfg, ma, mb, P, m_tiles, d->k, 1, (cudaStream_t)stream);
 }

@@ -238,3 +238,67 @@ def test_conv_cta_pairs(cuda, pairs, geo):
     wz = torch.zeros(k, c, 4, 4, device=cuda, requires_grad=True)
     gw = torch.autograd.grad(TF.conv2d(x, wz, None, stride=2, padding=1), wz, y)[0]
     assert rel_err(tc.wgrad(xp, yp), gw) <= 2e-3
+
+
+@pytest.mark.parametrize("geo", [(4, 128, 32, 256), (3, 128, 32, 256), (5, 128, 8, 64), (2, 128, 64, 128), (70, 128, 4, 192)])
+def test_transposed_dgrad(cuda, monkeypatch, geo):
+    """tc_dgradT_kernel (128 output channels as the MMA's M dimension), forced on for small / ragged cases: odd numbers
+    of pixel tiles, several images per tile (4x4 small maps), plain / bias + BatchNorm statistics / fused mask + sums."""
+    from eadgan_b200 import tc
+    from eadgan_b200._lib import ACT_LRELU
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "2")
+    n, c, h, k = geo
+    torch.manual_seed(9)
+    y = _bf(torch.randn(n, k, h // 2, h // 2, device=cuda))
+    w = _bf(torch.randn(k, c, 4, 4, device=cuda) * 0.05)
+    b = torch.randn(c, device=cuda)
+    yp, wpk = tc.to_padded(y), tc.pack_w(w, None, "dgrad")
+    ref = TF.conv_transpose2d(y, w, b, stride=2, padding=1)
+    stats = torch.zeros(2 * c, device=cuda, dtype=torch.float64)
+    out = tc.dgrad(yp, wpk, b, c, stats=stats)
+    assert rel_err(tc.from_padded(out), ref) <= 1e-2
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, -1].abs().max()) == 0
+    assert rel_err(stats[:c], ref.double().sum((0, 2, 3))) <= 2e-3
+    assert rel_err(stats[c:], (ref.double() ** 2).sum((0, 2, 3))) <= 2e-3
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "0")
+    old = tc.dgrad(yp, wpk, b, c)
+    assert rel_err(tc.from_padded(out), tc.from_padded(old)) <= 8e-3      # both round the same fp32 values to bf16
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "2")
+    act_out = _bf(torch.randn(n, c, h, h, device=cuda))
+    sigma = torch.tensor([1.25], device=cuda)
+    refm = TF.conv_transpose2d(y, w, None, stride=2, padding=1) / 1.25 * torch.where(act_out > 0, 1.0, 0.1)
+    sums = torch.zeros(c, device=cuda, dtype=torch.float64)
+    outm = tc.dgrad(yp, wpk, None, c, mask=tc.to_padded(act_out), mask_mode=ACT_LRELU, slope=0.1, stats=sums, stats_mode=2,
+                    sigma=sigma)
+    assert rel_err(tc.from_padded(outm), refm) <= 1e-2
+    assert float((sums - refm.double().sum((0, 2, 3))).abs().max() / refm.double().abs().sum((0, 2, 3)).max()) <= 2e-3
+
+
+@pytest.mark.parametrize("n", [5, 37])
+def test_channel_major_thin_fprop(cuda, monkeypatch, n):
+    """Conv2d(3,128,4,2,1) forward through the channel-major kernel (forced on for a ragged batch): bias + LeakyReLU +
+    1/sigma, and the masked variant with per-channel sums, against torch."""
+    from eadgan_b200 import tc
+    from eadgan_b200._lib import ACT_LRELU
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "2")
+    torch.manual_seed(10)
+    img = _bf(torch.rand(n, 3, 64, 64, device=cuda) * 2 - 1)
+    w = torch.randn(128, 3, 4, 4, device=cuda) * 0.1
+    b = torch.randn(128, device=cuda)
+    sigma = torch.tensor([1.6], device=cuda)
+    r = tc.thin_expand(img)
+    ref = TF.leaky_relu(TF.conv2d(img, _bf(w), None, stride=2, padding=1) / 1.6 + b[None, :, None, None], 0.1)
+    out = tc.thin_fprop(r, tc.thin_pack_w(w, "fprop"), b, 3, 128, ACT_LRELU, 0.1, sigma=sigma)
+    assert rel_err(tc.from_padded(out), ref) <= 1e-2
+    assert float(out[:, 0].abs().max()) == 0 and float(out[:, :, -1].abs().max()) == 0
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "0")
+    old = tc.thin_fprop(r, tc.thin_pack_w(w, "fprop"), b, 3, 128, ACT_LRELU, 0.1, sigma=sigma)
+    assert rel_err(tc.from_padded(out), tc.from_padded(old)) <= 8e-3
+    monkeypatch.setenv("EADGAN_TC_DGRADT", "2")
+    act_out = _bf(torch.randn(n, 128, 32, 32, device=cuda))
+    refm = TF.conv2d(img, _bf(w), None, stride=2, padding=1) * torch.where(act_out > 0, 1.0, 0.1)
+    sums = torch.zeros(128, device=cuda, dtype=torch.float64)
+    outm = tc.thin_fprop(r, tc.thin_pack_w(w, "fprop"), None, 3, 128, mask=tc.to_padded(act_out), mask_mode=ACT_LRELU,
+                         slope=0.1, stats=sums, stats_mode=2)
+    assert rel_err(tc.from_padded(outm), refm) <= 1e-2
+    assert float((sums - refm.double().sum((0, 2, 3))).abs().max() / refm.double().abs().sum((0, 2, 3)).max()) <= 2e-3
