@@ -160,6 +160,84 @@ __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ d
   }
 }
 
+// ---- small matrices (every dSprites / MNIST layer: <= 128 K weights): the whole forward in ONE block ----------------
+// The multi-kernel path above costs five launches of a few microseconds per layer and forward; the dSprites step has
+// 39 spectral-normalised layer forwards, i.e. ~200 of its ~630 launches.  Same arithmetic, one launch: W^T u (thread per
+// column), normalise, W v (warp per row), normalise, sigma.  The weight (<= 256 KB) is read from L2 three times.
+constexpr int SN_SMALL_MAX = 128 * 1024;    // weights
+constexpr int SN_SMALL_COLS = 4096, SN_SMALL_ROWS = 1024;
+__global__ void __launch_bounds__(1024) sn_small_fwd_kernel(const float* __restrict__ W, float* __restrict__ u,
+                                                            float* __restrict__ v, int rows, int cols, int do_pi, float eps,
+                                                            float* __restrict__ sigma) {
+  __shared__ float red[32];
+  __shared__ float vs[SN_SMALL_COLS];
+  __shared__ float ss[SN_SMALL_ROWS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (do_pi) {
+    for (int i = tid; i < rows; i += 1024) ss[i] = u[i];
+    __syncthreads();
+    float q = 0.f;
+    for (int j = tid; j < cols; j += 1024) {
+      float acc = 0.f;
+      for (int i = 0; i < rows; ++i) acc = fmaf(W[(int64_t)i * cols + j], ss[i], acc);
+      vs[j] = acc;
+      q = fmaf(acc, acc, q);
+    }
+    q = eg_block_sum(q, red);                       // (every thread gets the total)
+    const float inv = 1.f / fmaxf(sqrtf(q), eps);
+    for (int j = tid; j < cols; j += 1024) { const float x = vs[j] * inv; vs[j] = x; v[j] = x; }
+  } else {
+    for (int j = tid; j < cols; j += 1024) vs[j] = v[j];
+  }
+  __syncthreads();
+  for (int i = warp; i < rows; i += 32) {
+    const float* wr = W + (int64_t)i * cols;
+    float acc = 0.f;
+    for (int j = lane; j < cols; j += 32) acc = fmaf(wr[j], vs[j], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) ss[i] = acc;
+  }
+  __syncthreads();
+  if (do_pi) {
+    float q = 0.f;
+    for (int i = tid; i < rows; i += 1024) q = fmaf(ss[i], ss[i], q);
+    q = eg_block_sum(q, red);
+    const float inv = 1.f / fmaxf(sqrtf(q), eps);
+    float d = 0.f;
+    for (int i = tid; i < rows; i += 1024) { const float x = ss[i] * inv; u[i] = x; d = fmaf(x, ss[i], d); }
+    d = eg_block_sum(d, red);
+    if (tid == 0) *sigma = d;
+  } else {
+    float d = 0.f;
+    for (int i = tid; i < rows; i += 1024) d = fmaf(u[i], ss[i], d);
+    d = eg_block_sum(d, red);
+    if (tid == 0) *sigma = d;
+  }
+}
+
+// backward of a small layer in one block: dot = <dW, W>, then dW_orig = dW / sigma - dot / sigma^2 * u v^T
+__global__ void __launch_bounds__(1024) sn_small_bwd_kernel(const float* __restrict__ dW, const float* __restrict__ W,
+                                                            const float* __restrict__ u, const float* __restrict__ v,
+                                                            const float* __restrict__ sigma, int rows, int cols,
+                                                            float* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = rows * cols;
+  float d = 0.f;
+  for (int i = threadIdx.x; i < n; i += 1024) d = fmaf(dW[i], W[i], d);
+  d = eg_block_sum(d, red);
+  const float sg = *sigma;
+  const float coef = d / (sg * sg);
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const int r = i / cols, c = i - r * cols;
+    out[i] = dW[i] / sg - coef * u[r] * v[c];
+  }
+}
+
+bool sn_small(int rows, int cols) {
+  return (int64_t)rows * cols <= SN_SMALL_MAX && cols <= SN_SMALL_COLS && rows <= SN_SMALL_ROWS;
+}
+
 int grid_for(int64_t n) {
   int64_t b = (n + 1023) / 1024;
   const int64_t cap = 16 * (int64_t)eg_sm_count();
@@ -174,6 +252,16 @@ extern "C" int eadgan_spectral_norm_fwd(const float* w_orig, int rows, int cols,
   EG_REQUIRE(w_orig && u && v && sigma && scratch && rows > 0 && cols > 0, EADGAN_ERR_INVALID,
              "spectral_norm_fwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
+  if (sn_small(rows, cols)) {
+    sn_small_fwd_kernel<<<1, 1024, 0, st>>>(w_orig, u, v, rows, cols, do_power_iter ? 1 : 0, eps, sigma);
+    EG_LAUNCH_CHECK("sn_small_fwd_kernel");
+    if (w_sn) {
+      const int64_t n = (int64_t)rows * cols;
+      sn_scale_kernel<<<grid_for(n), 256, 0, st>>>(w_orig, sigma, w_sn, n);
+      EG_LAUNCH_CHECK("sn_scale_kernel");
+    }
+    return 0;
+  }
   int col_tiles = (cols + 127) / 128;
   int splits = (4 * eg_sm_count() + col_tiles - 1) / col_tiles;
   int max_splits = (rows + 15) / 16;
@@ -210,6 +298,11 @@ extern "C" int eadgan_spectral_norm_bwd(const float* dw_sn, const float* w_orig,
              EADGAN_ERR_INVALID, "spectral_norm_bwd: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = (int64_t)rows * cols;
+  if (sn_small(rows, cols)) {
+    sn_small_bwd_kernel<<<1, 1024, 0, st>>>(dw_sn, w_orig, u, v, sigma, rows, cols, dw_orig);
+    EG_LAUNCH_CHECK("sn_small_bwd_kernel");
+    return 0;
+  }
   const int parts = grid_for(n);
   sn_dot_kernel<<<parts, 256, 0, st>>>(dw_sn, w_orig, n, scratch);
   EG_LAUNCH_CHECK("sn_dot_kernel");

@@ -89,6 +89,15 @@ def make_pxy(B=8, seed=0, colored=False):
             "phases": fingerprint_log(log)}
 
 
+def make_approximator(n_iter=3, seed=0):
+    ns, log = R.run_approximator(n_iter, seed=seed)
+    return {"config": "approximator", "batch": 128, "iterations": n_iter, "seed": seed, "torch": torch.__version__,
+            "source": "MNIST/approximate_rpqmnxy.py executed by oracle/ref_runner.run_approximator (iteration count "
+                      "20001 -> %d)" % n_iter,
+            "losses": {"affine_loss": float(ns["affine_loss"])},        # the loss of the LAST iteration
+            "phases": fingerprint_log(log)}
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -96,7 +105,8 @@ def main():
                      ("dsprites_b6_seed0", lambda: make_dsprites(6, 0)), ("dsprites_b8_seed2", lambda: make_dsprites(8, 2)),
                      ("colored_b6_seed0", lambda: make_colored(6, 0)), ("colored_b8_seed1", lambda: make_colored(8, 1)),
                      ("mnist_b8_seed0", lambda: make_mnist(8, 0)), ("mnist_b64_seed1", lambda: make_mnist(64, 1)),
-                     ("pxy_b8_seed0", lambda: make_pxy(8, 0)), ("pxy_color_b8_seed0", lambda: make_pxy(8, 0, True))):
+                     ("pxy_b8_seed0", lambda: make_pxy(8, 0)), ("pxy_color_b8_seed0", lambda: make_pxy(8, 0, True)),
+                     ("approximator_it3_seed0", lambda: make_approximator(3, 0))):
         if sys.argv[1:] and not any(name.startswith(a) for a in sys.argv[1:]):
             continue
         g = fn()

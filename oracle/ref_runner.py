@@ -180,3 +180,31 @@ def run_script(name: str, batches, argv=(), seed=0, artefacts=None, pre_exec=Non
         for m in [m for m in sys.modules if m.startswith("utils_")]:
             del sys.modules[m]
     return ns, log
+
+
+def run_approximator(n_iter: int, seed=0):
+    """Execute MNIST/approximate_rpqmnxy.py (the script that pre-trains the affine approximator MLP, :111-153) for
+    ``n_iter`` iterations: the only change is the hard-coded iteration count ``range(20001)`` (:118).  Returns
+    (namespace, step_log) like run_script."""
+    path = os.path.join(REF_ROOT, "MNIST", "approximate_rpqmnxy.py")
+    tree = ast.parse(open(path).read())
+    hits = 0
+    for node in ast.walk(tree):
+        if isinstance(node, ast.Constant) and node.value == 20001:
+            node.value = int(n_iter)
+            hits += 1
+    assert hits == 1, "approximate_rpqmnxy.py: expected exactly one iteration-count literal"
+    code = compile(tree, path, "exec")
+    log = []
+    ns = {"__name__": "__main__"}
+    old_cwd = os.getcwd()
+    tmp = tempfile.mkdtemp(prefix="eadgan_ref_")
+    try:
+        os.chdir(tmp)
+        with _patched_torch(log), contextlib.redirect_stdout(open(os.devnull, "w")):
+            torch.manual_seed(seed)
+            np.random.seed(seed)
+            exec(code, ns)
+    finally:
+        os.chdir(old_cwd)
+    return ns, log

@@ -864,3 +864,41 @@ def step_pxy(st, img_u8, draws, record=True):
         rec["phases"][-1]["params_after"] = _params(st["opt_E"])
     rec["losses"] = {"affine_loss": loss.item()}
     return rec
+
+
+# --------------------------------------------------------------------------- #
+# pre-training of the MNIST affine approximator (MNIST/approximate_rpqmnxy.py) #
+# --------------------------------------------------------------------------- #
+
+
+def build_approximator(seed=0, device="cpu", dtype=torch.float32):
+    """MNIST/approximate_rpqmnxy.py:20-53: the MLP, MSELoss, Adam(lr 2e-4, betas (0.5, 0.999))."""
+    torch.manual_seed(seed)
+    A = MnistAffineApproximator().to(device=device, dtype=dtype)
+    return {"A": A, "opt": torch.optim.Adam(A.parameters(), lr=0.0002, betas=(0.5, 0.999))}
+
+
+def sample_approximator(rs: np.random.RandomState, batch=128):
+    """:121-122: codes (rand - 0.5) * 2, float32"""
+    return torch.tensor((rs.rand(batch, 7) - 0.5) * 2, dtype=torch.float32)
+
+
+def step_approximator(st, code, record=True):
+    """One iteration of MNIST/approximate_rpqmnxy.py:118-138: code -> 3x3 matrix (R Z Skew T, :77-108) -> its top two
+    rows -> MLP -> MSE against the 7 affine PARAMETERS (not the raw code)."""
+    A = st["A"]
+    dt = next(A.parameters()).dtype
+    code = code.to(next(A.parameters()).device, dt)
+    para = torch.stack((code[:, 0] * np.pi / 9, code[:, 1] * 0.2 + 1, code[:, 2] * 0.2 + 1, code[:, 3] * 0.2,
+                        code[:, 4] * 0.2, code[:, 5] * 0.1, code[:, 6] * 0.1), dim=1)
+    m = mnist_get_matrix(code)
+    st["opt"].zero_grad()
+    loss = nn.MSELoss()(A(torch.cat((m[:, 0], m[:, 1]), dim=1)), para)
+    loss.backward()
+    rec = {"loss": loss.item()}
+    if record:
+        rec["grads"] = _snap(st["opt"])
+    st["opt"].step()
+    if record:
+        rec["params_after"] = _params(st["opt"])
+    return rec

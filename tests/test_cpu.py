@@ -490,3 +490,33 @@ def test_affine_product_entry_points_have_no_cpu_fallback():
                affine.colored_relative_code):
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             fn(c, c)
+
+
+def test_approximator_oracle_reproduces_reference_golden():
+    """MNIST/approximate_rpqmnxy.py (pre-training of the affine approximator MLP): the restatement vs the fixture
+    produced by executing the script itself for 3 iterations (oracle/ref_runner.run_approximator)."""
+    from oracle import torch_oracle as O
+    with open(os.path.join(GOLDEN, "approximator_it3_seed0.json")) as f:
+        g = json.load(f)
+    st = O.build_approximator(seed=g["seed"])
+    rs = np.random.RandomState(g["seed"])
+    recs = [O.step_approximator(st, O.sample_approximator(rs, g["batch"])) for _ in range(g["iterations"])]
+    assert _close(recs[-1]["loss"], g["losses"]["affine_loss"], 1e-6)
+    for rec, gph in zip(recs, g["phases"]):
+        for t, fp in zip(rec["grads"], gph["grads"]):
+            _check_fp(t, fp, 1e-5)
+        for t, fp in zip(rec["params_after"], gph["params_after"]):
+            _check_fp(t, fp, 1e-5)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="needs the reference checkout (build container only)")
+def test_approximator_oracle_equals_the_executed_script():
+    from oracle import ref_runner as R, torch_oracle as O
+    ns, log = R.run_approximator(3, seed=1)
+    st = O.build_approximator(seed=1)
+    rs = np.random.RandomState(1)
+    for e in log:
+        rec = O.step_approximator(st, O.sample_approximator(rs, 128))
+        for a, b in zip(rec["params_after"], e["params_after"]):
+            assert torch.equal(a, b)
+    assert rec["loss"] == float(ns["affine_loss"])

@@ -4,9 +4,9 @@
 set -u
 tag=${1:-rXX}; shift
 mkdir -p gpurun_out
-python bench.py --batch 1024 --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_plain.log 2>&1 &&
+python bench.py --batch 1024 --steps 1 --warmup 3 --no-cpu-baseline --no-parity > gpurun_out/${tag}_plain.log 2>&1 &&
 EADGAN_PROFILE_WINDOW=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none \
-    --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --batch 1024 --steps 1 --warmup 3 --no-cpu-baseline \
+    --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --batch 1024 --steps 1 --warmup 3 --no-cpu-baseline --no-parity \
     > gpurun_out/${tag}_ncu_launches.log 2>&1
 i=0
 for spec in "$@"; do
