@@ -933,7 +933,28 @@ tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
           if (cn + pl + 8 * i < nvalid) mreg[i] = __ldg(reinterpret_cast<const uint4*>(P.mask + pix_off(cn + pl + 8 * i)));
         }
       };
-      if (P.mask_mode) load_mask(0);
+      if (P.mask_mode) {
+        load_mask(0);
+        // ... and the NEXT tile's mask rows are pulled into L2 now, a whole tile ahead: DRAM latency (twice the time
+        // a chunk takes) is then paid once per tile in the background instead of once per chunk in the foreground
+        const int nt = tile + gridDim.x;
+        if (nt < total_tiles) {
+          const int n_tile2 = nt % P.n_tiles, r2 = nt / P.n_tiles;
+          const int parity2 = r2 % P.parities, m_tile2 = (r2 / P.parities) * 2 + h;
+          const int b02 = (m_tile2 / P.tiles_y) * P.Tb, y02 = (m_tile2 % P.tiles_y) * P.Th;
+          const int py2 = parity2 >> 1, px2 = parity2 & 1;
+#pragma unroll 4
+          for (int q2 = 0; q2 < 16; ++q2) {
+            const int col = pl + 8 * q2;
+            const int xl = col & (P.Tw - 1), yl = (col >> lTw) & (P.Th - 1), bl = col >> (lTw + lTh);
+            if (b02 + bl < P.n && oct == 0) {       // one lane per 64-byte run
+              const int64_t o = (int64_t)(b02 + bl) * img_stride + (int64_t)(up * (y02 + yl) + py2 + 1) * row_stride +
+                                (int64_t)(up * xl + px2 + 1) * P.N_total + n_tile2 * 128 + quad * 32;
+              asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mask + o));
+            }
+          }
+        }
+      }
       const int buf = it & 1;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();

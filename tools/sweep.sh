@@ -14,6 +14,18 @@ run() {  # args: extra bench flags ; env assignments may precede through "env"
   fi
   echo "rc=$? $*" >> gpurun_out/${tag}_sweep_n${N}.err
 }
+if [ "$quick" = "scale" ]; then
+  # multi-GPU measurement set (GPU-minutes are charged N-fold): the default line with dp_parity, the 128-per-GPU
+  # points (weak and strong), colored (global batch 512) and the two ablations that say which exchange costs what
+  run
+  run --batch 128 --no-parity
+  run --global-batch 1024 --no-parity
+  run --config colored --no-parity
+  EADGAN_DP_ABLATE=grads run --no-parity
+  EADGAN_DP_ABLATE=syncbn run --no-parity
+elif [ "$quick" = "colored" ]; then
+  run --config colored --no-parity
+else
 # configs[3]: CelebA 1024 per GPU (weak), with parity (N=1) / dp_parity (N>1)
 run
 # configs[4]: per-GPU batch sweep (weak scaling)
@@ -24,11 +36,6 @@ if [ "$N" != "1" ]; then run --global-batch 1024; fi
 # configs[1] dSprites batch 256 per GPU; configs[2] colored, GLOBAL batch 512
 run --config dsprites
 run --config colored
-# which exchange costs what (N > 1): no gradient all-reduce / no SyncBN all-reduce (timing only)
-if [ "$N" != "1" ]; then
-  EADGAN_DP_ABLATE=grads run --no-parity
-  EADGAN_DP_ABLATE=syncbn run --no-parity
-  EADGAN_DP_ABLATE=grads,syncbn run --no-parity
 fi
 python - <<PY
 import json
