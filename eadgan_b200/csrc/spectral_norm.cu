@@ -160,11 +160,12 @@ __global__ void __launch_bounds__(256) sn_bwd_kernel(const float* __restrict__ d
   }
 }
 
-// ---- small matrices (every dSprites / MNIST layer: <= 128 K weights): the whole forward in ONE block ----------------
-// The multi-kernel path above costs five launches of a few microseconds per layer and forward; the dSprites step has
-// 39 spectral-normalised layer forwards, i.e. ~200 of its ~630 launches.  Same arithmetic, one launch: W^T u (thread per
-// column), normalise, W v (warp per row), normalise, sigma.  The weight (<= 256 KB) is read from L2 three times.
-constexpr int SN_SMALL_MAX = 128 * 1024;    // weights
+// ---- very small matrices (<= 16 K weights: the first convs and the Linear heads of the dSprites / MNIST nets): the
+// whole forward in ONE block instead of five launches.  Same arithmetic: W^T u (thread per column), normalise, W v
+// (warp per row), normalise, sigma.  Measured (r02v): with the threshold at 128 K weights the dSprites step got SLOWER
+// (5.68 -> 5.93 ms): one block walks a 64 x 1024 matrix three times with little memory parallelism, while the five
+// launches of the multi-kernel path use the whole chip and sit on a side stream anyway.
+constexpr int SN_SMALL_MAX = 16 * 1024;     // weights
 constexpr int SN_SMALL_COLS = 4096, SN_SMALL_ROWS = 1024;
 __global__ void __launch_bounds__(1024) sn_small_fwd_kernel(const float* __restrict__ W, float* __restrict__ u,
                                                             float* __restrict__ v, int rows, int cols, int do_pi, float eps,
@@ -179,6 +180,7 @@ __global__ void __launch_bounds__(1024) sn_small_fwd_kernel(const float* __restr
     float q = 0.f;
     for (int j = tid; j < cols; j += 1024) {
       float acc = 0.f;
+#pragma unroll 8
       for (int i = 0; i < rows; ++i) acc = fmaf(W[(int64_t)i * cols + j], ss[i], acc);
       vs[j] = acc;
       q = fmaf(acc, acc, q);
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(1024) sn_small_fwd_kernel(const float* __restr
   for (int i = warp; i < rows; i += 32) {
     const float* wr = W + (int64_t)i * cols;
     float acc = 0.f;
+#pragma unroll 8
     for (int j = lane; j < cols; j += 32) acc = fmaf(wr[j], vs[j], acc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);

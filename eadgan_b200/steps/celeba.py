@@ -116,11 +116,19 @@ class CelebAStep:
         g_loss = self.bce(validity, valid)
         g_loss.backward()
         chain.set_trainable(D, True)
-        self._snap(self.opt_G, record, "G")
-        self.opt_G.step()
-        self._after(self.opt_G, record)
-        if after_phase is not None:
-            after_phase(0)
+        # Optimiser steps are DEFERRED to the last point where nothing has read the weights they change (same
+        # arithmetic, independent work reordered): phase D never touches G (it sees gen.detach(), computed above), so
+        # opt_G.step() -- which under data parallelism first waits for the all-reduce of G's gradients -- runs after
+        # phase D's backward, and that all-reduce overlaps the whole of phase D; opt_D.step() runs after the info phase's
+        # G forward, which hides the all-reduce of D's last buckets.  With a recorder or a test hook attached the
+        # reference's literal order is kept.
+        defer = record is None and after_phase is None
+        if not defer:
+            self._snap(self.opt_G, record, "G")
+            self.opt_G.step()
+            self._after(self.opt_G, record)
+            if after_phase is not None:
+                after_phase(0)
 
         # phase D -- :353-366
         self.opt_D.zero_grad()
@@ -128,16 +136,24 @@ class CelebAStep:
         _, _, fake_pred = D(gen.detach())
         d_loss = (self.bce(real_pred, valid) + self.bce(fake_pred, fake)) / 2
         d_loss.backward()
-        self._snap(self.opt_D, record, "D")
-        self.opt_D.step()
-        self._after(self.opt_D, record)
-        if after_phase is not None:
-            after_phase(1)
-        chain.prefetch_spectral_norm(D.main, 3)     # the info phase's three D forwards (weights fixed until opt_info.step)
+        if defer:
+            self.opt_G.step()
+        else:
+            self._snap(self.opt_D, record, "D")
+            self.opt_D.step()
+            self._after(self.opt_D, record)
+            if after_phase is not None:
+                after_phase(1)
+            chain.prefetch_spectral_norm(D.main, 3)     # the info phase's three D forwards (weights fixed until opt_info.step)
 
         # phase info -- :375-401
-        self.opt_info.zero_grad()
+        if not defer:
+            self.opt_info.zero_grad()
         gen = G(z, onehot, code)
+        if defer:
+            self.opt_D.step()
+            chain.prefetch_spectral_norm(D.main, 3)
+            self.opt_info.zero_grad()
         pred_label, pred_code, _ = D(gen)
         info = self.ce(pred_label, labels) + self.mse(pred_code, code)
         _, transform_code, _ = D(scaled)

@@ -166,3 +166,28 @@ def test_phase_g_skips_discriminator_weight_gradients(cuda):
     assert not any(seen[1])                  # after phase D: every D parameter has one
     assert all(p.requires_grad for p in step.D.parameters())
     assert all(g is not None for g in rec[2]["grads"])      # the info phase owns G and D
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_deferred_optimizer_steps_equal_the_literal_order(cuda, prec):
+    """CelebAStep defers opt_G.step() past phase D and opt_D.step() past the info phase's G forward (nothing reads the
+    weights in between; under data parallelism the gradient all-reduces hide behind that work).  Two iterations in the
+    deferred order must leave exactly the losses, weights, BatchNorm statistics and spectral-norm vectors of the
+    reference's literal order (kept whenever a test hook is attached)."""
+    import os
+    import numpy as np
+    from eadgan_b200.steps.celeba import CelebAStep
+    from oracle import torch_oracle as O
+    os.environ["EADGAN_PRECISION"] = prec
+    a, b = CelebAStep(seed=5, device=cuda), CelebAStep(seed=5, device=cuda)
+    for it in range(2):
+        imgs = O.synth_celeba_images(16, it).to(cuda)
+        d = O.sample_celeba(np.random.RandomState(it), 16)
+        args = (imgs, d["z"].to(cuda), d["code"].to(cuda), d["labels"].to(cuda))
+        la = a(*args)                                   # deferred
+        lb = b(*args, after_phase=lambda i: None)       # literal
+        for k in la:
+            assert float(la[k]) == float(lb[k]), (it, k)
+    for net_a, net_b in ((a.G, b.G), (a.D, b.D)):
+        for (k, va), (_, vb) in zip(net_a.state_dict().items(), net_b.state_dict().items()):
+            assert torch.equal(va, vb), k

@@ -15,10 +15,10 @@ run() {  # args: extra bench flags ; env assignments may precede through "env"
   echo "rc=$? $*" >> gpurun_out/${tag}_sweep_n${N}.err
 }
 if [ "$quick" = "scale" ]; then
-  # multi-GPU measurement set (GPU-minutes are charged N-fold): the default line with dp_parity, the 128-per-GPU
-  # points (weak and strong), colored (global batch 512) and the two ablations that say which exchange costs what
+  # multi-GPU measurement set (GPU-minutes are charged N-fold): the default line with dp_parity, GLOBAL batch 1024
+  # (= 128 per GPU at N = 8: the strong-scaling point), colored (global batch 512) and the two ablations that say
+  # which exchange costs what
   run
-  run --batch 128 --no-parity
   run --global-batch 1024 --no-parity
   run --config colored --no-parity
   EADGAN_DP_ABLATE=grads run --no-parity
