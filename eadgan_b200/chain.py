@@ -328,6 +328,22 @@ def _r64(v):
     return (v + 63) // 64 * 64
 
 
+class _Arena:
+    """one zero-filled fp64 buffer handed out in slices (16-byte aligned)"""
+
+    def __init__(self, n, dev):
+        self.buf = torch.zeros(n + 2, device=dev, dtype=torch.float64) if n > 0 else None
+        self.off = 0
+
+    def take(self, n):
+        n2 = (n + 1) // 2 * 2
+        if self.buf is None or self.off + n2 > self.buf.numel():
+            return torch.zeros(n, device=self.buf.device if self.buf is not None else "cuda", dtype=torch.float64)
+        out = self.buf[self.off:self.off + n]
+        self.off += n2
+        return out
+
+
 class _ChainFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, stages, srcs, *params):
@@ -336,6 +352,10 @@ class _ChainFn(torch.autograd.Function):
         cur = _Buf(x.contiguous(), "ext")
         saved = []
         pi = 0
+        # ONE zero fill for all per-channel fp64 statistics vectors of this forward (a fill kernel per BatchNorm layer
+        # was ~40 launches of a few microseconds per step)
+        arena = _Arena(sum(2 * (s_.conv.weight.shape[0] if s_.kind == "conv" else s_.conv.weight.shape[1])
+                           for s_ in stages if s_.bn is not None), dev)
         for si, st in enumerate(stages):
             w, b = params[pi], params[pi + 1]
             pi += 2
@@ -349,7 +369,7 @@ class _ChainFn(torch.autograd.Function):
             out_shape = (d.n, d.k, d.p, d.q) if st.kind == "conv" else (d.n, d.c, d.h, d.w)
             cout = out_shape[1]
             epi_act = st.act if st.bn is None else (ACT_NONE, 0.0)
-            stats = torch.zeros(2 * cout, device=dev, dtype=torch.float64) if st.bn is not None else None
+            stats = arena.take(2 * cout) if st.bn is not None else None
             wc = w.contiguous()
             impl = _impl(st, d, last)
             rec = {"d": d, "w": wc, "has_b": b is not None, "impl": impl, "pi": pi - (4 if st.bn is not None else 2)}
@@ -464,6 +484,7 @@ class _ChainFn(torch.autograd.Function):
         g_masked = False
         db_sums = None   # fp64 per-channel sums of g, accumulated by the epilogue of the kernel that produced g
         grads = []
+        arena = _Arena(sum(3 * max(sv_["d"].k, sv_["d"].c) for sv_ in saved), dev)   # every fp64 sum vector of this backward
         for si in range(len(stages) - 1, -1, -1):
             st, sv = stages[si], saved[si]
             d, impl = sv["d"], sv["impl"]
@@ -477,7 +498,7 @@ class _ChainFn(torch.autograd.Function):
             need_db = sv["has_b"] and ctx.needs_input_grad[3 + sv["pi"] + 1]
             # ---- 1. gradient w.r.t. the conv output (pre-BN / pre-activation) ----------------
             if st.bn is not None:
-                sums = torch.zeros(2 * cout, device=dev, dtype=torch.float64)
+                sums = arena.take(2 * cout)
                 gd, xd, yd = t4(g.view()), t4(sv["pre"].view()), t4(sv["y"].view())
                 call("eadgan_bn_bwd_reduce", C.byref(gd), C.byref(xd), C.byref(yd), n, cout, oh, ow, ptr(sv["mean"]),
                      ptr(sv["invstd"]), ptr(sv["gamma"]), ptr(sv["beta"]), st.act[0], float(st.act[1]), ptr(sums), st_)
@@ -524,7 +545,7 @@ class _ChainFn(torch.autograd.Function):
             want_sums = (need_dx and prev is not None and prev.bn is None and saved[si - 1]["has_b"]
                          and ctx.needs_input_grad[3 + saved[si - 1]["pi"] + 1]
                          and (fuse or prev.act[0] == ACT_NONE) and in_shape[1] <= 1024)
-            sums_buf = torch.zeros(in_shape[1], device=dev, dtype=torch.float64) if want_sums else None
+            sums_buf = arena.take(in_shape[1]) if want_sums else None
             sums_used = False
             # ---- 2./3. weight gradient and input gradient -----------------------------------------
             if impl == "thin":

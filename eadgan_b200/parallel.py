@@ -30,7 +30,9 @@ _state = None
 
 
 class DataParallel:
-    def __init__(self, rank, world_size, device, bucket_bytes=32 << 20, overlap=True):
+    def __init__(self, rank, world_size, device, bucket_bytes=None, overlap=True):
+        if bucket_bytes is None:
+            bucket_bytes = int(os.environ.get("EADGAN_DP_BUCKET_MB", "32")) << 20
         self.rank, self.world_size, self.device = rank, world_size, device
         self.bucket_elems = max(1, bucket_bytes // 4)
         self.overlap = overlap  # on CPU (gloo, tests) the buckets are reduced asynchronously too, without a side stream
