@@ -259,7 +259,6 @@ struct TcParams {
   int stat_channels;   // length of one statistics vector (stats = [sum | sum of squares])
   int thin;            // fprop on a <= 4-channel image: ONE 64-wide k block, A boxes from the row-expanded buffer
   int bias_len;        // number of bias entries (n_store, or dense_C for the scatter GEMM)
-  int dbg;             // experiments only (EADGAN_TC_DBG): bit 0 skip the global stores, bit 1 skip the staging tile too
   const float* sigma;  // spectral-norm sigma (device scalar) or NULL: accumulators are multiplied by 1/sigma, so the
                        // packed bf16 operand can be the UN-normalised weight_orig (cached across forwards)
 };
@@ -768,15 +767,39 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // pixel the 32 lanes of a warp hold 32 consecutive channels = one 64-byte run of the NHWC tensors, so the fused
 // activation-backward mask is read, and the result written, as full 32-byte sectors.
 // ------------------------------------------------------------------------------------
+template <int EW>
 struct DgTCfg {
   static constexpr int STAGE_BYTES = 3 * A_BYTES;                 // two pixel tiles + one weight tile, 48 KB
   static constexpr int STAGES = 4;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + 8 * 2048 /* staging */ + 2 * 128 * 2 * 8 /* stats */;
+  static constexpr int CH = EW == 8 ? 32 : 16;                    // pixels per epilogue chunk
+  static constexpr int STG_BYTES = CH * 64;                       // per warp: [CH pixels][32 channels] bf16
+  static constexpr int STAT_BYTES = (EW / 4) * 128 * 2 * 4;       // [column group][channel][sum, sum of squares] fp32
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 + 256 + EW * STG_BYTES + STAT_BYTES;
 };
 
-__global__ void __launch_bounds__(320, 1)
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// SPEC fixes the epilogue's mode switches at compile time for the three shapes the training step launches (the
+// epilogue is bound by its instruction stream: ncu r02y, 414 instructions per 32x32 chunk of which 160 are the
+// arithmetic and the stores): 0 = generic (every switch read from P), 1 = thin fprop + bias + LeakyReLU,
+// 2 = dgrad + fused LeakyReLU-backward mask, 3 = dgrad + BatchNorm statistics.
+// EW = epilogue warps (8 or 16): warp (quad, group) owns channels quad*32.. and 256 / (EW/4) pixel columns.
+template <int SPEC, int EW>
+__global__ void __launch_bounds__(64 + EW * 32, 1)
 tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w, const TcParams P) {
-  using C = DgTCfg;
+  using C = DgTCfg<EW>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
@@ -793,7 +816,7 @@ tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], 8); }
+      for (int b = 0; b < 2; ++b) { mbar_init(&tmem_full_bar[b], 1); mbar_init(&tmem_empty_bar[b], EW); }
       fence_barrier_init();
     }
     __syncwarp();
@@ -871,45 +894,54 @@ tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       }
     }
   } else {
-    // ===== epilogue: lane = output channel, column = pixel.  Warp (quad, h): channels quad*32.., pixel tile h =====
-    // Global traffic goes through a per-warp 2 KB staging tile [32 pixels][32 channels] bf16: the fused mask is read,
-    // and the result written, with 16-byte accesses (lane -> pixel lane/4 + 8 i, channel octet lane%4: every
-    // instruction covers eight 64-byte runs), while the per-channel view (lane = channel) uses conflict-free 2-byte
-    // shared-memory accesses.
-    const int quad = warp & 3;
-    const int h = (warp - 2) >> 2;
+    // ===== epilogue: lane = output channel, column = pixel.  Warp (quad, grp): channels quad*32.., columns grp*GCOLS.. =====
+    // Global traffic goes through a per-warp staging tile [CH pixels][32 channels] bf16: the fused mask is read, and
+    // the result written, with 16-byte accesses (lane -> pixel lane/4 + 8 i, channel octet lane%4: every instruction
+    // covers eight 64-byte runs), while the per-channel view (lane = channel) uses 2-byte shared-memory accesses.
+    constexpr int GROUPS = EW / 4, GCOLS = 256 / GROUPS, CH = C::CH, NI = CH / 8;
+    const int act = SPEC == 0 ? P.act : (SPEC == 1 ? (int)EADGAN_ACT_LRELU : 0);
+    const int mask_mode = SPEC == 0 ? P.mask_mode : (SPEC == 2 ? (int)EADGAN_ACT_LRELU : 0);
+    const int want_stats = SPEC == 0 ? P.want_stats : (SPEC == 3 ? 1 : 0);
+    // dgrad writes every second pixel of the big map (one parity), fprop all of them
+    const int up = SPEC == 0 ? (P.mode == MODE_DGRAD ? 2 : 1) : (SPEC == 1 ? 1 : 2);
+    const int quad = warp & 3, grp = (warp - 2) >> 2;
+    const int h = (grp * GCOLS) >> 7, cbase = (grp * GCOLS) & 127;   // pixel-tile half and first column inside it
     const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
     const int lTw = 31 - __clz(P.Tw), lTh = 31 - __clz(P.Th);
-    const int64_t row_stride = (int64_t)(P.OW + 2) * P.N_total, img_stride = (int64_t)(P.OH + 2) * row_stride;
+    const int row_stride = (P.OW + 2) * P.N_total, img_stride = (P.OH + 2) * row_stride;   // elements, < 2^31
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(P.out);
-    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + (warp - 2) * 2048;
-    double* stat_s = reinterpret_cast<double*>(smem + C::STAGES * C::STAGE_BYTES + 256 + 8 * 2048);   // [2 h][128][2]
+    uint8_t* stg = smem + C::STAGES * C::STAGE_BYTES + 256 + (warp - 2) * C::STG_BYTES;
+    float* stat_s = reinterpret_cast<float*>(smem + C::STAGES * C::STAGE_BYTES + 256 + EW * C::STG_BYTES);   // [grp][128][2]
     const int et = threadIdx.x - 64;
     float s1 = 0.f, s2 = 0.f;      // running per-channel statistics of this lane's channel (fp32 per CTA, fp64 across)
     int cur_blk = -1;
-    auto flush = [&]() {           // all 8 epilogue warps: fold the two pixel-tile halves, one fp64 atomic per channel
-      stat_s[(h * 128 + quad * 32 + lane) * 2 + 0] = (double)s1;
-      stat_s[(h * 128 + quad * 32 + lane) * 2 + 1] = (double)s2;
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+    auto flush = [&]() {           // all epilogue warps: fold the column groups, one fp64 atomic per channel
+      stat_s[(grp * 128 + quad * 32 + lane) * 2 + 0] = s1;
+      stat_s[(grp * 128 + quad * 32 + lane) * 2 + 1] = s2;
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       if (et < 128 && cur_blk >= 0) {
         const int gch = cur_blk * 128 + et;
         if (gch < P.stat_channels) {
-          atomicAdd(&P.stats[gch], stat_s[et * 2] + stat_s[(128 + et) * 2]);
-          if (P.want_stats == 1) atomicAdd(&P.stats[P.stat_channels + gch], stat_s[et * 2 + 1] + stat_s[(128 + et) * 2 + 1]);
+          double a1 = 0.0, a2 = 0.0;
+#pragma unroll
+          for (int g = 0; g < GROUPS; ++g) { a1 += (double)stat_s[(g * 128 + et) * 2]; a2 += (double)stat_s[(g * 128 + et) * 2 + 1]; }
+          atomicAdd(&P.stats[gch], a1);
+          if (want_stats == 1) atomicAdd(&P.stats[P.stat_channels + gch], a2);
         }
       }
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, %0;" ::"n"(EW * 32) : "memory");
       s1 = 0.f; s2 = 0.f;
     };
     const int pl = lane >> 2, oct = lane & 3;          // 16-byte view: pixel pl + 8 i of the chunk, channel octet oct
-    const int up = P.mode == MODE_DGRAD ? 2 : 1;       // dgrad writes every second pixel of the big map (one parity), fprop all
+    uint8_t* stg16 = stg + pl * 64 + oct * 16;         // ... its slot in the staging tile (+ 512 i)
+    uint8_t* stg2 = stg + lane * 2;                    // channel view: pixel j of the chunk at + 64 j
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int n_tile = tile % P.n_tiles, r = tile / P.n_tiles;
       const int parity = r % P.parities, m_tile = (r / P.parities) * 2 + h;
       const int py = parity >> 1, px = parity & 1;
       const int b0 = (m_tile / P.tiles_y) * P.Tb, y0 = (m_tile % P.tiles_y) * P.Th;
-      if (P.want_stats && n_tile != cur_blk) {         // tile -> channel block is the same for every warp of the CTA
+      if (want_stats && n_tile != cur_blk) {           // tile -> channel block is the same for every warp of the CTA
         if (cur_blk >= 0) flush();
         cur_blk = n_tile;
       }
@@ -918,131 +950,116 @@ tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
       // columns are ordered (image, row, x): the valid ones (image < n) are a prefix
       int nvalid = (P.n - b0) << (lTw + lTh);
       nvalid = nvalid < 0 ? 0 : (nvalid > 128 ? 128 : nvalid);
-      auto pix_off = [&](int col) -> int64_t {         // element offset of (pixel of column `col`, first channel of this warp)
+      // element offset of (first pixel of the tile, this lane's channel octet); pixels of the tile are 32-bit offsets from it
+      const int64_t tbase = (int64_t)b0 * img_stride + (int64_t)(up * y0 + py + 1) * row_stride +
+                            (int64_t)((px + 1) * P.N_total + n_tile * 128 + quad * 32 + oct * 8);
+      __nv_bfloat16* out_t = out + tbase;
+      const __nv_bfloat16* mask_t = P.mask + tbase;
+      auto rel = [&](int col) -> int {
         const int xl = col & (P.Tw - 1), yl = (col >> lTw) & (P.Th - 1), bl = col >> (lTw + lTh);
-        return (int64_t)(b0 + bl) * img_stride + (int64_t)(up * (y0 + yl) + py + 1) * row_stride +
-               (int64_t)(up * xl + px + 1) * P.N_total + n_tile * 128 + quad * 32 + oct * 8;
+        return bl * img_stride + up * (yl * row_stride + xl * P.N_total);
       };
       // the fused mask is software-pipelined one chunk ahead: its loads are in flight while the accumulator of the
       // current chunk is read and processed (the first chunk's while this warp still waits for the MMAs)
-      uint4 mreg[4];
+      uint4 mreg[NI];
       auto load_mask = [&](int cn) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < NI; ++i) {
           mreg[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (cn + pl + 8 * i < nvalid) mreg[i] = __ldg(reinterpret_cast<const uint4*>(P.mask + pix_off(cn + pl + 8 * i)));
+          if (cn + pl + 8 * i < nvalid) mreg[i] = __ldg(reinterpret_cast<const uint4*>(mask_t + rel(cn + pl + 8 * i)));
         }
       };
-      if (P.mask_mode) {
-        load_mask(0);
-        // ... and the NEXT tile's mask rows are pulled into L2 now, a whole tile ahead: DRAM latency (twice the time
-        // a chunk takes) is then paid once per tile in the background instead of once per chunk in the foreground
-        const int nt = tile + gridDim.x;
-        if (nt < total_tiles) {
-          const int n_tile2 = nt % P.n_tiles, r2 = nt / P.n_tiles;
-          const int parity2 = r2 % P.parities, m_tile2 = (r2 / P.parities) * 2 + h;
-          const int b02 = (m_tile2 / P.tiles_y) * P.Tb, y02 = (m_tile2 % P.tiles_y) * P.Th;
-          const int py2 = parity2 >> 1, px2 = parity2 & 1;
-#pragma unroll 4
-          for (int q2 = 0; q2 < 16; ++q2) {
-            const int col = pl + 8 * q2;
-            const int xl = col & (P.Tw - 1), yl = (col >> lTw) & (P.Th - 1), bl = col >> (lTw + lTh);
-            if (b02 + bl < P.n && oct == 0) {       // one lane per 64-byte run
-              const int64_t o = (int64_t)(b02 + bl) * img_stride + (int64_t)(up * (y02 + yl) + py2 + 1) * row_stride +
-                                (int64_t)(up * xl + px2 + 1) * P.N_total + n_tile2 * 128 + quad * 32;
-              asm volatile("prefetch.global.L2 [%0];" ::"l"(P.mask + o));
-            }
-          }
-        }
-      }
+      if (mask_mode) load_mask(cbase);
       const int buf = it & 1;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * 256 + h * 128) + ((uint32_t)(quad * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        int64_t goff[4];
+      for (int c0 = cbase; c0 < cbase + GCOLS; c0 += CH) {
+        int goff[NI];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) goff[i] = pix_off(c0 + pl + 8 * i);
-        if (P.mask_mode) {
+        for (int i = 0; i < NI; ++i) goff[i] = rel(c0 + pl + 8 * i);
+        if (mask_mode) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stg + (pl + 8 * i) * 64 + oct * 16) = mreg[i];
-          if (c0 + 32 < 128) load_mask(c0 + 32);
+          for (int i = 0; i < NI; ++i) *reinterpret_cast<uint4*>(stg16 + 512 * i) = mreg[i];
+          if (c0 + CH < cbase + GCOLS) load_mask(c0 + CH);
         }
-        float v[32];
-        tmem_ld32(acc + (uint32_t)c0, v);
-        if (c0 + 32 >= 128) {   // this warp's columns are all in registers: hand the accumulator back
+        float v[CH];
+        if (CH == 32) tmem_ld32(acc + (uint32_t)c0, v); else tmem_ld16(acc + (uint32_t)c0, v);
+        if (c0 + CH >= cbase + GCOLS) {   // this warp's columns are all in registers: hand the accumulator back
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
         __syncwarp();
         // every mode switch is uniform for the launch: decided ONCE per chunk, outside the element loops
-        const bool all_valid = c0 + 32 <= nvalid;
+        const bool all_valid = c0 + CH <= nvalid;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaf(v[j], inv_sigma, bias);
-        if (P.want_stats == 1) {
+        for (int j = 0; j < CH; ++j) v[j] = fmaf(v[j], inv_sigma, bias);
+        if (want_stats == 1) {
           if (all_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
+            for (int j = 0; j < CH; ++j) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CH; ++j)
               if (c0 + j < nvalid) { s1 += v[j]; s2 = fmaf(v[j], v[j], s2); }
           }
         }
-        if (P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU) {
-          const float sl = P.act == EADGAN_ACT_RELU ? 0.f : P.slope;
+        if (act == EADGAN_ACT_RELU || act == EADGAN_ACT_LRELU) {
+          const float sl = act == EADGAN_ACT_RELU ? 0.f : P.slope;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
-        } else if (P.act == EADGAN_ACT_TANH) {
+          for (int j = 0; j < CH; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * sl;
+        } else if (act == EADGAN_ACT_TANH) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
-        } else if (P.act == EADGAN_ACT_SIGMOID) {
+          for (int j = 0; j < CH; ++j) v[j] = tanhf(v[j]);
+        } else if (act == EADGAN_ACT_SIGMOID) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
+          for (int j = 0; j < CH; ++j) v[j] = 1.f / (1.f + expf(-v[j]));
         }
-        if (P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU) {
-          const float sl = P.mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
+        if (mask_mode == EADGAN_ACT_RELU || mask_mode == EADGAN_ACT_LRELU) {
+          const float sl = mask_mode == EADGAN_ACT_RELU ? 0.f : P.slope;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {   // saved OUTPUT y > 0 <=> pre-activation > 0: sign / zero test on the raw bf16 bits
-            const uint32_t mb = *reinterpret_cast<const uint16_t*>(stg + j * 64 + lane * 2);
+          for (int j = 0; j < CH; ++j) {   // saved OUTPUT y > 0 <=> pre-activation > 0: sign / zero test on the raw bf16 bits
+            const uint32_t mb = *reinterpret_cast<const uint16_t*>(stg2 + j * 64);
             if ((mb & 0x8000u) != 0 || (mb & 0x7fffu) == 0) v[j] *= sl;
           }
-        } else if (P.mask_mode) {
+        } else if (mask_mode) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float m = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg + j * 64 + lane * 2));
-            v[j] *= eg_act_grad(m, P.mask_mode, P.slope);
+          for (int j = 0; j < CH; ++j) {
+            const float m = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(stg2 + j * 64));
+            v[j] *= eg_act_grad(m, mask_mode, P.slope);
           }
         }
-        if (P.want_stats == 2) {
+        if (want_stats == 2) {
           if (all_valid) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) s1 += v[j];
+            for (int j = 0; j < CH; ++j) s1 += v[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
+            for (int j = 0; j < CH; ++j)
               if (c0 + j < nvalid) s1 += v[j];
           }
         }
-        __syncwarp();           // every lane has read its mask column: the staging tile can take the result
-        if (!(P.dbg & 2)) {
+        if (mask_mode) __syncwarp();   // every lane has read its mask column: the staging tile can take the result
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            *reinterpret_cast<__nv_bfloat16*>(stg + j * 64 + lane * 2) = __float2bfloat16_rn(v[j]);
-        } else if (v[3] == 123.456f) out[0] = __float2bfloat16_rn(v[5]);
+        for (int j = 0; j < CH; ++j)
+          *reinterpret_cast<__nv_bfloat16*>(stg2 + j * 64) = __float2bfloat16_rn(v[j]);
         __syncwarp();
-        if (!(P.dbg & 1)) {
+        if (all_valid) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < NI; ++i)
+            *reinterpret_cast<uint4*>(out_t + goff[i]) = *reinterpret_cast<const uint4*>(stg16 + 512 * i);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NI; ++i)
             if (c0 + pl + 8 * i < nvalid)
-              *reinterpret_cast<uint4*>(out + goff[i]) = *reinterpret_cast<const uint4*>(stg + (pl + 8 * i) * 64 + oct * 16);
+              *reinterpret_cast<uint4*>(out_t + goff[i]) = *reinterpret_cast<const uint4*>(stg16 + 512 * i);
         }
         __syncwarp();           // ... before the next chunk overwrites the tile
       }
     }
-    if (P.want_stats) flush();
+    if (want_stats) flush();
   }
   tc_fence_before();
   __syncthreads();
@@ -1442,16 +1459,32 @@ int opt_in_smem(K kernel, int bytes, std::atomic<uint64_t>& done) {
   return 0;
 }
 
-int launch_channel_major(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P, cudaStream_t st) {
+template <int SPEC, int EW>
+int launch_channel_major_t(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P, cudaStream_t st) {
   static std::atomic<uint64_t> opted{0};
-  if (int e = opt_in_smem(tc_dgradT_kernel, DgTCfg::SMEM, opted)) return e;
+  if (int e = opt_in_smem(tc_dgradT_kernel<SPEC, EW>, DgTCfg<EW>::SMEM, opted)) return e;
   const int total = P.parities * P.m_tiles * P.n_tiles;
   const int units = eg_tc_units();
   const int waves = (total + units - 1) / units;
   const int grid = (total + waves - 1) / waves;
-  tc_dgradT_kernel<<<grid, 320, DgTCfg::SMEM, st>>>(mx, mw, P);
+  tc_dgradT_kernel<SPEC, EW><<<grid, 64 + EW * 32, DgTCfg<EW>::SMEM, st>>>(mx, mw, P);
   EG_LAUNCH_CHECK("tc_dgradT_kernel");
   return 0;
+}
+
+int launch_channel_major(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P, cudaStream_t st) {
+  // the three epilogue shapes of the training step get a specialised instance (see tc_dgradT_kernel)
+  int spec = 0;
+  if (P.thin && P.act == EADGAN_ACT_LRELU && !P.mask_mode && !P.want_stats) spec = 1;
+  else if (!P.thin && P.mode == MODE_DGRAD && P.mask_mode == EADGAN_ACT_LRELU && !P.want_stats && !P.act) spec = 2;
+  else if (!P.thin && P.mode == MODE_DGRAD && !P.mask_mode && P.want_stats == 1 && !P.act) spec = 3;
+  int ew = 16;
+  if (const char* e = getenv("EADGAN_TC_EW")) { if (atoi(e) == 8 || atoi(e) == 16) ew = atoi(e); }
+  if (const char* e = getenv("EADGAN_TC_SPEC")) { if (atoi(e) == 0) spec = 0; }
+#define EG_CM(S, W) if (spec == S && ew == W) return launch_channel_major_t<S, W>(mx, mw, P, st);
+  EG_CM(0, 8) EG_CM(1, 8) EG_CM(2, 8) EG_CM(3, 8) EG_CM(0, 16) EG_CM(1, 16) EG_CM(2, 16) EG_CM(3, 16)
+#undef EG_CM
+  return EADGAN_ERR_INVALID;
 }
 
 bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
@@ -1647,7 +1680,6 @@ extern "C" int eadgan_tc_dgrad(const eadgan_tc_desc* d, const void* dy_pad, cons
     P.OH = d->h; P.OW = d->w; P.bias = bias; P.out = dx; P.mask = (const __nv_bfloat16*)mask; P.stats = stats;
     P.sigma = sigma; P.n_store = d->c; P.stat_channels = d->c;
     P.m_tiles = (m_tiles + 1) / 2; P.n_tiles = d->c / 128; P.parities = 4;
-    if (const char* e = getenv("EADGAN_TC_DBG")) P.dbg = atoi(e);
     EG_REQUIRE(!P.mask_mode || mask, EADGAN_ERR_INVALID, "tc_dgrad: mask_mode without mask");
     EG_REQUIRE(!P.want_stats || stats, EADGAN_ERR_INVALID, "tc_dgrad: want_stats without stats");
     CUtensorMap mx, mw;
