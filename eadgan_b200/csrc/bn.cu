@@ -12,6 +12,7 @@
 //                          (halo-padded private buffers: sc==1, sw==c, any sh/sn)
 // Algorithmic bytes / element: stats 4 (fp32) or 2 (bf16) read; apply read+write;
 // bwd_reduce 2 reads; bwd_apply 2 reads + 1 write.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace {
@@ -377,6 +378,49 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_nhwc8_kernel(BwdArgs a, Nhw
   for (int i = threadIdx.x; i < 2 * g.c; i += 256) atomicAdd(&sums[i], sh[i]);
 }
 
+// forward statistics (sum x, sum x^2) of a bf16 NHWC buffer whose producer could not fuse them (dense 1x1 -> 4x4
+// layers): same access pattern as the kernels above instead of one 2-byte load per thread and iteration
+__global__ void __launch_bounds__(256) bn_stats_nhwc8_kernel(eadgan_tensor4 x, Nhwc8 g, double* sums) {
+  __shared__ double sh[2 * 1024];
+  for (int i = threadIdx.x; i < 2 * g.c; i += 256) sh[i] = 0.0;
+  __syncthreads();
+  const int ch0 = (threadIdx.x % g.cv) * 8;
+  float s0[8], s1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+  const int rows = g.n * g.h;
+  for (int row0 = blockIdx.x * NHWC8_U; row0 < rows; row0 += gridDim.x * NHWC8_U) {
+    const uint4* xr[NHWC8_U];
+#pragma unroll
+    for (int u = 0; u < NHWC8_U; ++u) {
+      const int row = min(row0 + u, rows - 1);
+      const int b = row / g.h, y = row - b * g.h;
+      xr[u] = row_ptr(x, b, y);
+    }
+    for (int v = threadIdx.x; v < g.row_vecs; v += 256) {
+      uint4 raw[NHWC8_U];
+#pragma unroll
+      for (int u = 0; u < NHWC8_U; ++u) raw[u] = __ldg(xr[u] + v);
+#pragma unroll
+      for (int u = 0; u < NHWC8_U; ++u) {
+        if (row0 + u < rows) {
+          float f[8];
+          bf8_to_f32(raw[u], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { s0[j] += f[j]; s1[j] = fmaf(f[j], f[j], s1[j]); }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    atomicAdd(&sh[ch0 + j], (double)s0[j]);
+    atomicAdd(&sh[g.c + ch0 + j], (double)s1[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * g.c; i += 256) atomicAdd(&sums[i], sh[i]);
+}
+
 template <bool GATE_FROM_X>
 __global__ void __launch_bounds__(256) bn_bwd_apply_nhwc8_kernel(BwdArgs a, Nhwc8 g) {
   ChanParams p;
@@ -453,7 +497,8 @@ bool nhwc8_ok(const Geo& g, const eadgan_tensor4* const* ts, int nt) {
 }
 Nhwc8 make_nhwc8(const Geo& g) { return Nhwc8{g.n, g.c, g.h, g.w, g.c / 8, g.w * g.c / 8}; }
 int nhwc8_grid(const Geo& g) {
-  const int groups = (g.n * g.h + NHWC8_U - 1) / NHWC8_U, cap = 8 * eg_sm_count();
+  static const int per_sm = [] { const char* e = getenv("EADGAN_BN_BLOCKS_PER_SM"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 2; }();
+  const int groups = (g.n * g.h + NHWC8_U - 1) / NHWC8_U, cap = per_sm * eg_sm_count();
   return groups < cap ? groups : cap;
 }
 
@@ -535,6 +580,12 @@ extern "C" int eadgan_bn_stats(const eadgan_tensor4* x, int n, int c, int h, int
   const eadgan_tensor4* ts[] = {x};
   EG_REQUIRE(x && sums, EADGAN_ERR_INVALID, "bn_stats: NULL argument");
   if (int e = make_geo(&g, n, c, h, w, ts, 1, "bn_stats")) return e;
+  if (nhwc8_ok(g, ts, 1)) {
+    const int groups = (g.n * g.h + NHWC8_U - 1) / NHWC8_U, cap = 4 * eg_sm_count();   // one wave, four blocks per SM
+    bn_stats_nhwc8_kernel<<<groups < cap ? groups : cap, 256, 0, (cudaStream_t)stream>>>(*x, make_nhwc8(g), sums);
+    EG_LAUNCH_CHECK("bn_stats_nhwc8_kernel");
+    return 0;
+  }
   bn_stats_kernel<<<reduce_grid(g), 256, 0, (cudaStream_t)stream>>>(*x, g, sums);
   EG_LAUNCH_CHECK("bn_stats_kernel");
   return 0;

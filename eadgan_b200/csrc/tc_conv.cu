@@ -793,8 +793,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
 
 // SPEC fixes the epilogue's mode switches at compile time for the three shapes the training step launches (the
 // epilogue is bound by its instruction stream: ncu r02y, 414 instructions per 32x32 chunk of which 160 are the
-// arithmetic and the stores): 0 = generic (every switch read from P), 1 = thin fprop + bias + LeakyReLU,
-// 2 = dgrad + fused LeakyReLU-backward mask, 3 = dgrad + BatchNorm statistics.
+// arithmetic and the stores): 0 = generic (every switch read from P), 1 = bias + (Leaky)ReLU (the thin fprop),
+// 2 = fused (Leaky)ReLU-backward mask, 3 = BatchNorm statistics; ReLU is LeakyReLU with slope 0 (set by the launcher).
 // EW = epilogue warps (8 or 16): warp (quad, group) owns channels quad*32.. and 256 / (EW/4) pixel columns.
 template <int SPEC, int EW>
 __global__ void __launch_bounds__(64 + EW * 32, 1)
@@ -903,7 +903,7 @@ tc_dgradT_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constan
     const int mask_mode = SPEC == 0 ? P.mask_mode : (SPEC == 2 ? (int)EADGAN_ACT_LRELU : 0);
     const int want_stats = SPEC == 0 ? P.want_stats : (SPEC == 3 ? 1 : 0);
     // dgrad writes every second pixel of the big map (one parity), fprop all of them
-    const int up = SPEC == 0 ? (P.mode == MODE_DGRAD ? 2 : 1) : (SPEC == 1 ? 1 : 2);
+    const int up = P.mode == MODE_DGRAD ? 2 : 1;
     const int quad = warp & 3, grp = (warp - 2) >> 2;
     const int h = (grp * GCOLS) >> 7, cbase = (grp * GCOLS) & 127;   // pixel-tile half and first column inside it
     const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
@@ -1281,16 +1281,23 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   __shared__ float tile[16][65];
   const int ko = blockIdx.y, c0 = blockIdx.x * 64;
   const int Ktot = 16 * c;
-  for (int e = threadIdx.x; e < 16 * 64; e += 256) {
-    const int tap = e / 64, cl = e % 64;  // tap = ((a*2+b)*2+dy)*2+dx
-    if (c0 + cl < c) {
+  {   // one float4 (4 channels of one tap) per thread, the split loop unrolled: 4 x 16 B in flight per thread
+    const int tap = threadIdx.x >> 4, cl = (threadIdx.x & 15) * 4;  // tap = ((a*2+b)*2+dy)*2+dx
+    if (c0 + cl < c) {                                              // c is a multiple of 32: whole float4s
       const int t3 = tap >> 1, dx = tap & 1;
       const int64_t col = (int64_t)t3 * 2 * c + (int64_t)dx * c + c0 + cl;
-      float s = 0.f;
-      for (int sp = 0; sp < splits; ++sp) s += partial[((int64_t)sp * k + ko) * Ktot + col];
+      const float4* src = reinterpret_cast<const float4*>(partial + (int64_t)ko * Ktot + col);
+      const int64_t sp_stride = (int64_t)k * Ktot / 4;
+      float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+      for (int sp = 0; sp < splits; ++sp) {
+        const float4 v = __ldg(src + sp * sp_stride);
+        s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      }
       const int dy = t3 & 1, bt = (t3 >> 1) & 1, at = t3 >> 2;
       const int ky = 2 * at + dy, kx = 2 * bt + dx;
-      tile[ky * 4 + kx][cl] = s;
+      float* trow = tile[ky * 4 + kx];
+      trow[cl] = s.x; trow[cl + 1] = s.y; trow[cl + 2] = s.z; trow[cl + 3] = s.w;
     }
   }
   __syncthreads();
@@ -1472,15 +1479,24 @@ int launch_channel_major_t(const CUtensorMap& mx, const CUtensorMap& mw, const T
   return 0;
 }
 
-int launch_channel_major(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P, cudaStream_t st) {
+int launch_channel_major(const CUtensorMap& mx, const CUtensorMap& mw, const TcParams& P0, cudaStream_t st) {
   // the three epilogue shapes of the training step get a specialised instance (see tc_dgradT_kernel)
+  TcParams P = P0;
+  const bool act_lrelu = P.act == EADGAN_ACT_RELU || P.act == EADGAN_ACT_LRELU;
+  const bool mask_lrelu = P.mask_mode == EADGAN_ACT_RELU || P.mask_mode == EADGAN_ACT_LRELU;
   int spec = 0;
-  if (P.thin && P.act == EADGAN_ACT_LRELU && !P.mask_mode && !P.want_stats) spec = 1;
-  else if (!P.thin && P.mode == MODE_DGRAD && P.mask_mode == EADGAN_ACT_LRELU && !P.want_stats && !P.act) spec = 2;
-  else if (!P.thin && P.mode == MODE_DGRAD && !P.mask_mode && P.want_stats == 1 && !P.act) spec = 3;
+  if (act_lrelu && !P.mask_mode && !P.want_stats) {
+    spec = 1;
+    if (P.act == EADGAN_ACT_RELU) { P.act = EADGAN_ACT_LRELU; P.slope = 0.f; }
+  } else if (mask_lrelu && !P.want_stats && !P.act) {
+    spec = 2;
+    if (P.mask_mode == EADGAN_ACT_RELU) { P.mask_mode = EADGAN_ACT_LRELU; P.slope = 0.f; }
+  } else if (!P.mask_mode && P.want_stats == 1 && !P.act) {
+    spec = 3;
+  }
   int ew = 16;
   if (const char* e = getenv("EADGAN_TC_EW")) { if (atoi(e) == 8 || atoi(e) == 16) ew = atoi(e); }
-  if (const char* e = getenv("EADGAN_TC_SPEC")) { if (atoi(e) == 0) spec = 0; }
+  if (const char* e = getenv("EADGAN_TC_SPEC")) { if (atoi(e) == 0) { spec = 0; P = P0; } }
 #define EG_CM(S, W) if (spec == S && ew == W) return launch_channel_major_t<S, W>(mx, mw, P, st);
   EG_CM(0, 8) EG_CM(1, 8) EG_CM(2, 8) EG_CM(3, 8) EG_CM(0, 16) EG_CM(1, 16) EG_CM(2, 16) EG_CM(3, 16)
 #undef EG_CM
@@ -2044,13 +2060,15 @@ struct ThinDgParams {
 
 constexpr int THIN_STAGES = 6;
 constexpr int THIN_STAGE_BYTES = A_BYTES + 64 * BLOCK_K * 2;   // 16 KB + 8 KB
-constexpr int THIN_SMEM = THIN_STAGES * THIN_STAGE_BYTES + 1024 + 256 + 2 * 4 * 12 * 32 * 4;
+constexpr int THIN_SMEM = THIN_STAGES * THIN_STAGE_BYTES + 1024 + 256 + 2 * 2 * 4 * 12 * 32 * 4;
 
-// Z[128 pixels][64] = y_tile[128][k] . Wt^T, then col2im.  192 threads: warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+// Z[128 pixels][64] = y_tile[128][k] . Wt^T, then col2im.  320 threads: warp 0 TMA, warp 1 MMA, warps 2..5 and 6..9
+// two epilogue groups, one per accumulator buffer (even / odd tiles of the CTA): the kernel is bound by the epilogue
+// (ncu r02aa: 9 % occupancy, 0.25 eligible warps per scheduler with a single group), two tiles are drained at once.
 // (TMEM lane quadrant q = warp & 3 = tile row q; lane = x).  Input row m owns output rows 2m, 2m+1:
 //   out[2m  ][2j+b] = Xr_m[ky 1][b] + Xr_{m-1}[ky 3][b]        Xr[ky][0] = Z[ky][kx 1] + Z_{j-1}[ky][kx 3]
 //   out[2m+1][2j+b] = Xr_m[ky 2][b] + Xr_{m+1}[ky 0][b]        Xr[ky][1] = Z[ky][kx 2] + Z_{j+1}[ky][kx 0]
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const ThinDgParams P) {
   extern __shared__ uint8_t smem_raw[];
@@ -2060,7 +2078,7 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   uint64_t* tmem_full_bar = empty_bar + THIN_STAGES;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  float* xs = reinterpret_cast<float*>(smem + THIN_STAGES * THIN_STAGE_BYTES + 256);  // [2 buf][4 rows][12][32]
+  float* xs = reinterpret_cast<float*>(smem + THIN_STAGES * THIN_STAGE_BYTES + 256);  // [2 groups][2][4 rows][12][32]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = P.n * P.tiles_per_img;
@@ -2124,6 +2142,7 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
   } else {
     const int quad = warp & 3;   // tile row: 0 = r0-1 (halo), 1 = r0, 2 = r0+1, 3 = r0+2 (halo)
+    const int grp = (warp - 2) >> 2;   // epilogue group = accumulator buffer = parity of the CTA's tile counter
     const float inv_sigma = P.sigma ? 1.f / __ldg(P.sigma) : 1.f;
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
     if (P.bias) {
@@ -2131,9 +2150,9 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       for (int c = 0; c < 4; ++c) if (c < P.c_real) bias[c] = __ldg(&P.bias[c]);
     }
     const int OW = 64, OH = 2 * P.p;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int buf = it & 1;
+    int it = grp;
+    for (int tile = blockIdx.x + grp * gridDim.x; tile < total_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int buf = grp;             // == it & 1
       const int b = tile / P.tiles_per_img, r0 = (tile % P.tiles_per_img) * 2;
       mbar_wait(&tmem_full_bar[buf], (it >> 1) & 1);
       tc_fence_after();
@@ -2159,7 +2178,9 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
       }
       // ---- y direction (neighbouring warps) through shared memory ----
-      float* mine = xs + ((buf * 4 + quad) * 12) * 32;
+      // exchange buffer alternates per use: the group's barrier of use i+1 separates the reads of use i from the writes of use i+2
+      float* xg = xs + ((grp * 2 + ((it >> 1) & 1)) * 4 * 12) * 32;
+      float* mine = xg + (quad * 12) * 32;
 #pragma unroll
       for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
@@ -2167,11 +2188,11 @@ tc_thin_dgrad_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           mine[(0 * 6 + bb * 3 + c) * 32 + lane] = xr[0][bb][c];   // what the row ABOVE needs (its out[2m+1])
           mine[(1 * 6 + bb * 3 + c) * 32 + lane] = xr[3][bb][c];   // what the row BELOW needs (its out[2m])
         }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory"); else asm volatile("bar.sync 2, 128;" ::: "memory");
       if (quad == 1 || quad == 2) {
         const int m = r0 + quad - 1;
-        const float* above = xs + ((buf * 4 + quad - 1) * 12) * 32;   // row m-1: its ky = 3 sums
-        const float* below = xs + ((buf * 4 + quad + 1) * 12) * 32;   // row m+1: its ky = 0 sums
+        const float* above = xg + ((quad - 1) * 12) * 32;   // row m-1: its ky = 3 sums
+        const float* below = xg + ((quad + 1) * 12) * 32;   // row m+1: its ky = 0 sums
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
           if (c < P.c_real) {
@@ -2344,7 +2365,7 @@ extern "C" int eadgan_tc_thin_dgrad(const eadgan_tc_desc* d, const void* dy_pad,
   const int sms = eg_sm_count();
   const int waves = (total + sms - 1) / sms;
   const int grid = (total + waves - 1) / waves;
-  tc_thin_dgrad_kernel<<<grid, 192, THIN_SMEM, (cudaStream_t)stream>>>(ma, mb, P);
+  tc_thin_dgrad_kernel<<<grid, 320, THIN_SMEM, (cudaStream_t)stream>>>(ma, mb, P);
   EG_LAUNCH_CHECK("tc_thin_dgrad_kernel");
   return 0;
 }
