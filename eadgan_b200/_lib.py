@@ -135,6 +135,16 @@ def bump_weights_epoch():
     weights_epoch += 1
 
 
+step_serial = 0    # one number per Adam.step() call; the parameters it updates carry it as ``_eadgan_stepped`` so that
+                   # only THEIR cached packs / prefetched spectral-norm results go stale (phase G's step leaves D's alone)
+
+
+def next_step_serial():
+    global step_serial
+    step_serial += 1
+    return step_serial
+
+
 _lib = None
 launches = 0  # number of C-ABI compute calls issued (bench.py reports kernel launches from it)
 

@@ -151,6 +151,49 @@ def prefetch_spectral_norm(seq, count=1):
                 conv.__dict__.setdefault("_eadgan_sn_queue", []).append((entry, ev, tag))
 
 
+pack_prefetch_enabled = os.environ.get("EADGAN_PACK_PREFETCH", "1") != "0"
+
+
+def prefetch_packs(module):
+    """Re-pack the bf16 GEMM operands of every conv stack inside ``module`` now, on the side stream.
+
+    The packs depend only on the raw weights (sigma of a spectral-normalised layer is applied in the kernel
+    epilogue), so a step driver calls this right after the optimiser step that changed them; the ~30 small
+    permutation kernels per step then overlap the main stream's work instead of preceding the first GEMM that needs
+    them.  The layouts are the ones each parameter was consumed in so far (tc._note_use), i.e. nothing happens on the
+    first step.  ``try_run`` waits on the recorded event before the stack's first kernel."""
+    if precision() != "bf16" or not prefetch_enabled or not pack_prefetch_enabled:
+        return
+    todo = []
+    for seq in module.modules():
+        if not isinstance(seq, torch.nn.Sequential):
+            continue
+        stages = _plan(seq)
+        if stages is None:
+            continue
+        for st in stages:
+            p = getattr(st.conv, "weight_orig", None)
+            if p is None:
+                p = st.conv.weight
+            if isinstance(p, torch.nn.Parameter) and p.is_cuda and getattr(p, "_eadgan_pack_uses", None):
+                todo.append((st.conv, p))
+    if not todo:
+        return
+    dev = todo[0][1].device
+    cur = torch.cuda.current_stream()
+    side = _sn_streams.get(dev)
+    if side is None:
+        side = _sn_streams[dev] = torch.cuda.Stream(device=dev)
+    side.wait_stream(cur)          # the optimiser step (and every earlier consumer of the old packs) comes first
+    with torch.cuda.stream(side):
+        for _, p in todo:
+            tc.prefetch_packs(p)
+        ev = torch.cuda.Event()
+        ev.record(side)
+    for conv, _ in todo:
+        conv.__dict__["_eadgan_pack_ev"] = ev
+
+
 def set_trainable(module, flag):
     """Step drivers freeze the networks the current phase's optimiser does not own (celebA/EAD-GAN_celebA.py:334-345:
     phase G back-propagates THROUGH D, and the reference also computes D's weight gradients there, which
@@ -176,6 +219,9 @@ def try_run(seq, x):
         return None  # eval-mode BN: per-op path
     params, srcs = [], []
     for st in stages:
+        pack_ev = st.conv.__dict__.pop("_eadgan_pack_ev", None)
+        if pack_ev is not None:        # operands re-packed ahead of time on the side stream (prefetch_packs)
+            torch.cuda.current_stream().wait_event(pack_ev)
         queue = st.conv.__dict__.get("_eadgan_sn_queue")
         if queue:
             # this forward's power iteration was issued ahead of time (prefetch_spectral_norm): adopt its results

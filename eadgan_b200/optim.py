@@ -67,6 +67,7 @@ class Adam(torch.optim.Optimizer):
         reduced = self._dp.reduce(self) if self._dp is not None else None  # {param: reduced grad}
         gscale = 1.0 if self._dp is None else 1.0 / self._dp.world_size
         capturing = torch.cuda.is_available() and torch.cuda.is_current_stream_capturing()
+        serial = L.next_step_serial()
         if capturing:
             if self._step_dev is None:
                 raise RuntimeError("eadgan_b200.Adam: call prepare_capture() before capturing step() in a CUDA graph")
@@ -100,7 +101,7 @@ class Adam(torch.optim.Optimizer):
                     self._launch(ps, gs, ms, vs, group, t, gscale)
                     ps, gs, ms, vs = [], [], [], []
                     t = st["step"]
-                p._eadgan_stepped = L.weights_epoch + 1   # spectral-norm results prefetched before this step are stale
+                p._eadgan_stepped = serial   # its cached packs and prefetched spectral-norm results are stale now
                 ps.append(p)
                 gs.append(g if g.is_contiguous() else g.contiguous())
                 ms.append(st["exp_avg"])
@@ -110,7 +111,6 @@ class Adam(torch.optim.Optimizer):
         if not capturing and self._step_dev is not None:
             # an eager step between graph replays: the device counter the captured step() reads must advance too
             call("eadgan_adam_advance", C.c_void_p(self._step_dev.data_ptr()), stream())
-        L.bump_weights_epoch()   # parameters changed through raw pointers: packed-weight caches are stale
         return loss
 
     @staticmethod

@@ -9,10 +9,11 @@ is the reference's and every forward/backward runs on the sm_100a kernels.
 from __future__ import annotations
 
 import itertools
+import os
 
 import torch
 
-from .. import affine, chain, functional as Fn
+from .. import affine, chain, functional as Fn, parallel
 from .. import nn as nn
 from ..optim import Adam
 from .._lib import ACT_SIGMOID
@@ -69,6 +70,8 @@ class CelebAStep:
         self.opt_info = Adam(itertools.chain(self.G.parameters(), self.D.parameters()), lr=0.0002, betas=betas)
         self.bce, self.mse, self.ce = nn.BCELoss(), nn.MSELoss(), nn.CrossEntropyLoss()
         self.device = torch.device(device)
+        e = os.environ.get("EADGAN_DEFER_D")       # experiments: force the placement of opt_D.step() (see __call__)
+        self._defer_D = None if e is None else e != "0"
 
     def optimizers(self):
         return [self.opt_G, self.opt_D, self.opt_info]
@@ -103,6 +106,10 @@ class CelebAStep:
         # the reference computes and then discards at :353) are never launched.  The weight tensors W / sigma are
         # produced by the prefetch, hence one prefetch with D frozen (phase G's forward) and two with D trainable
         chain.clear_prefetch(D.main)          # leftovers of an aborted step, if any
+        # ... and so do the bf16 operand packs of both networks (the last opt_info.step() changed G and D): G's are
+        # needed first, D's overlap G's forward
+        chain.prefetch_packs(G)
+        chain.prefetch_packs(D)
         chain.set_trainable(D, False)
         chain.prefetch_spectral_norm(D.main, 1)
         chain.set_trainable(D, True)
@@ -119,10 +126,13 @@ class CelebAStep:
         # Optimiser steps are DEFERRED to the last point where nothing has read the weights they change (same
         # arithmetic, independent work reordered): phase D never touches G (it sees gen.detach(), computed above), so
         # opt_G.step() -- which under data parallelism first waits for the all-reduce of G's gradients -- runs after
-        # phase D's backward, and that all-reduce overlaps the whole of phase D; opt_D.step() runs after the info phase's
-        # G forward, which hides the all-reduce of D's last buckets.  With a recorder or a test hook attached the
-        # reference's literal order is kept.
+        # phase D's backward, and that all-reduce overlaps the whole of phase D; under data parallelism opt_D.step()
+        # runs after the info phase's G forward, which hides the all-reduce of D's last buckets (on one device it
+        # stays where it is, and the side-stream work it releases -- D's operand packs and power iterations --
+        # overlaps that G forward instead).  With a recorder or a test hook attached the reference's literal order
+        # is kept.
         defer = record is None and after_phase is None
+        defer_D = defer and (self._defer_D if self._defer_D is not None else parallel.get() is not None)
         if not defer:
             self._snap(self.opt_G, record, "G")
             self.opt_G.step()
@@ -138,20 +148,23 @@ class CelebAStep:
         d_loss.backward()
         if defer:
             self.opt_G.step()
-        else:
+            chain.prefetch_packs(G)
+        if not defer_D:
             self._snap(self.opt_D, record, "D")
             self.opt_D.step()
             self._after(self.opt_D, record)
             if after_phase is not None:
                 after_phase(1)
+            chain.prefetch_packs(D)
             chain.prefetch_spectral_norm(D.main, 3)     # the info phase's three D forwards (weights fixed until opt_info.step)
 
         # phase info -- :375-401
-        if not defer:
+        if not defer_D:
             self.opt_info.zero_grad()
         gen = G(z, onehot, code)
-        if defer:
+        if defer_D:
             self.opt_D.step()
+            chain.prefetch_packs(D)
             chain.prefetch_spectral_norm(D.main, 3)
             self.opt_info.zero_grad()
         pred_label, pred_code, _ = D(gen)

@@ -115,11 +115,13 @@ _pack_cache = {}
 def pack_w_cached(param, direction="fprop", c_alloc=None):
     """pack_w of a PARAMETER object (a G weight, or the weight_orig of a spectral-normalised layer), cached until
     the parameter changes: torch's version counter catches in-place torch ops (load_state_dict, stock
-    optimisers), _lib.weights_epoch catches our fused Adam (which updates through raw pointers).  Entries are
+    optimisers), the ``_eadgan_stepped`` serial our fused Adam leaves on every parameter it updates (through raw
+    pointers) catches that one, _lib.weights_epoch everything wholesale (load_state_dict, graph replays).  Entries are
     tied to the parameter OBJECT (weak reference), never to an address that a later tensor could reuse.  Code
     that rewrites a parameter through ``.data`` must call eadgan_b200.invalidate_caches()."""
     key = (id(param), direction, c_alloc)
-    token = (param._version, param.data_ptr(), L.weights_epoch)
+    token = (param._version, param.data_ptr(), L.weights_epoch, getattr(param, "_eadgan_stepped", 0))
+    _note_use(param, "wide", direction, c_alloc)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0]() is param and hit[1] == token:
         return hit[2]
@@ -128,6 +130,25 @@ def pack_w_cached(param, direction="fprop", c_alloc=None):
         weakref.finalize(param, _pack_cache.pop, key, None)
     _pack_cache[key] = (weakref.ref(param), token, out)
     return out
+
+
+def _note_use(param, kind, direction, c_alloc):
+    """remember which operand layouts a parameter is consumed in, so that they can be rebuilt ahead of time"""
+    uses = getattr(param, "_eadgan_pack_uses", None)
+    if uses is None:
+        uses = set()
+        param._eadgan_pack_uses = uses
+    uses.add((kind, direction, c_alloc))
+
+
+def prefetch_packs(param):
+    """Rebuild, on the CURRENT stream, every operand layout ``param`` was consumed in so far (no-op for layouts whose
+    cached pack is still current).  chain.prefetch_packs calls this on a side stream right after an optimiser step."""
+    for kind, direction, c_alloc in tuple(getattr(param, "_eadgan_pack_uses", ())):
+        if kind == "thin":
+            thin_pack_w_cached(param, direction)
+        else:
+            pack_w_cached(param, direction, c_alloc)
 
 
 def invalidate_caches():
@@ -252,7 +273,8 @@ def thin_pack_w(w, direction):
 
 def thin_pack_w_cached(param, direction):
     key = (id(param), "thin_" + direction, None)
-    token = (param._version, param.data_ptr(), L.weights_epoch)
+    token = (param._version, param.data_ptr(), L.weights_epoch, getattr(param, "_eadgan_stepped", 0))
+    _note_use(param, "thin", direction, None)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0]() is param and hit[1] == token:
         return hit[2]

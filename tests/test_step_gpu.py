@@ -168,11 +168,13 @@ def test_phase_g_skips_discriminator_weight_gradients(cuda):
     assert all(g is not None for g in rec[2]["grads"])      # the info phase owns G and D
 
 
+@pytest.mark.parametrize("defer_D", [False, True])
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-def test_deferred_optimizer_steps_equal_the_literal_order(cuda, prec):
-    """CelebAStep defers opt_G.step() past phase D and opt_D.step() past the info phase's G forward (nothing reads the
-    weights in between; under data parallelism the gradient all-reduces hide behind that work).  Two iterations in the
-    deferred order must leave exactly the losses, weights, BatchNorm statistics and spectral-norm vectors of the
+def test_deferred_optimizer_steps_equal_the_literal_order(cuda, prec, defer_D):
+    """CelebAStep defers opt_G.step() past phase D and -- under data parallelism, forced here -- opt_D.step() past the
+    info phase's G forward (nothing reads the weights in between; the gradient all-reduces hide behind that work), and
+    re-packs the GEMM operands / runs the spectral-norm iterations ahead of time on a side stream.  Two iterations in
+    the deferred order must leave exactly the losses, weights, BatchNorm statistics and spectral-norm vectors of the
     reference's literal order (kept whenever a test hook is attached)."""
     import os
     import numpy as np
@@ -180,7 +182,8 @@ def test_deferred_optimizer_steps_equal_the_literal_order(cuda, prec):
     from oracle import torch_oracle as O
     os.environ["EADGAN_PRECISION"] = prec
     a, b = CelebAStep(seed=5, device=cuda), CelebAStep(seed=5, device=cuda)
-    for it in range(2):
+    a._defer_D = defer_D
+    for it in range(3):
         imgs = O.synth_celeba_images(16, it).to(cuda)
         d = O.sample_celeba(np.random.RandomState(it), 16)
         args = (imgs, d["z"].to(cuda), d["code"].to(cuda), d["labels"].to(cuda))

@@ -302,3 +302,29 @@ def test_channel_major_thin_fprop(cuda, monkeypatch, n):
                          slope=0.1, stats=sums, stats_mode=2)
     assert rel_err(tc.from_padded(outm), refm) <= 1e-2
     assert float((sums - refm.double().sum((0, 2, 3))).abs().max() / refm.double().abs().sum((0, 2, 3)).max()) <= 2e-3
+
+
+def test_pack_cache_goes_stale_per_parameter(cuda):
+    """The bf16 operand packs are cached per parameter.  Our fused Adam updates weights through raw pointers, so it
+    leaves a serial on exactly the parameters it stepped: their packs are rebuilt, everybody else's stay cached
+    (phase G's optimiser step does not make D re-pack).  tc.prefetch_packs rebuilds the layouts used so far."""
+    from eadgan_b200 import tc
+    from eadgan_b200.optim import Adam
+    torch.manual_seed(0)
+    w1 = torch.nn.Parameter(torch.randn(64, 32, 4, 4, device=cuda))
+    w2 = torch.nn.Parameter(torch.randn(64, 32, 4, 4, device=cuda))
+    a1, b1 = tc.pack_w_cached(w1, "fprop", 32), tc.pack_w_cached(w2, "fprop", 32)
+    b1d = tc.pack_w_cached(w2, "dgrad", 32)
+    assert tc.pack_w_cached(w2, "fprop", 32) is b1
+    opt = Adam([w2], lr=0.1)
+    w2.grad = torch.ones_like(w2)
+    opt.step()
+    assert tc.pack_w_cached(w1, "fprop", 32) is a1              # not stepped: still cached
+    tc.prefetch_packs(w2)                                       # rebuilds both layouts w2 was consumed in
+    b2, b2d = tc.pack_w_cached(w2, "fprop", 32), tc.pack_w_cached(w2, "dgrad", 32)
+    assert b2 is not b1 and b2d is not b1d
+    assert torch.equal(b2, tc.pack_w(w2.detach(), None, "fprop", 32))
+    assert torch.equal(b2d, tc.pack_w(w2.detach(), None, "dgrad", 32))
+    assert not torch.equal(b2, b1)
+    tc.invalidate_caches()
+    assert tc.pack_w_cached(w1, "fprop", 32) is not a1          # wholesale invalidation still works
