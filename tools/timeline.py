@@ -74,6 +74,40 @@ def main():
     lines.append("largest gaps: us, at ms, after -> before")
     for g in sorted(idle, reverse=True)[:25]:
         lines.append(f"  {g[0]:8.1f} us at {g[3] / 1e3:7.3f} ms  {g[1][:60]} -> {g[2][:60]}")
+    # collectives: how much of every NCCL kernel runs with NO compute kernel beside it (exposed), by kernel
+    nccl = [e for e in evs if "nccl" in e.name.lower()]
+    if nccl:
+        comp = sorted((e.time_range.start, e.time_range.end) for e in evs if "nccl" not in e.name.lower())
+        merged = []
+        for s_, e_ in comp:
+            if merged and s_ <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], e_)
+            else:
+                merged.append([s_, e_])
+        def covered(a, b):
+            tot = 0.0
+            for s_, e_ in merged:
+                if e_ <= a:
+                    continue
+                if s_ >= b:
+                    break
+                tot += min(b, e_) - max(a, s_)
+            return tot
+        lines.append("collectives (NCCL kernels): count, total us, exposed us (no compute kernel running beside them)")
+        agg = {}
+        for e in nccl:
+            a, b = e.time_range.start, e.time_range.end
+            d = agg.setdefault(e.name[:70], [0, 0.0, 0.0])
+            d[0] += 1
+            d[1] += b - a
+            d[2] += (b - a) - covered(a, b)
+        for name, (cnt, us, ex) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            lines.append(f"  {name:70s} {cnt:4d} {us:9.1f} {ex:9.1f}")
+        big = sorted(nccl, key=lambda e: -(e.time_range.end - e.time_range.start))[:12]
+        lines.append("longest collectives: us, exposed us, at ms")
+        for e in big:
+            a, b = e.time_range.start, e.time_range.end
+            lines.append(f"  {b - a:8.1f} {(b - a) - covered(a, b):8.1f} at {(a - t0) / 1e3:7.3f} ms  {e.name[:60]}")
     by = {}
     for e in evs:
         d = by.setdefault(e.name, [0, 0.0])
