@@ -161,7 +161,7 @@ def prefetch_packs(module):
     epilogue), so a step driver calls this right after the optimiser step that changed them; the ~30 small
     permutation kernels per step then overlap the main stream's work instead of preceding the first GEMM that needs
     them.  The layouts are the ones each parameter was consumed in so far (tc._note_use), i.e. nothing happens on the
-    first step.  ``try_run`` waits on the recorded event before the stack's first kernel."""
+    first step.  Every pack built here carries an event which its consumer's stream waits on (tc._adopt)."""
     if precision() != "bf16" or not prefetch_enabled or not pack_prefetch_enabled:
         return
     todo = []
@@ -176,22 +176,18 @@ def prefetch_packs(module):
             if p is None:
                 p = st.conv.weight
             if isinstance(p, torch.nn.Parameter) and p.is_cuda and getattr(p, "_eadgan_pack_uses", None):
-                todo.append((st.conv, p))
+                todo.append(p)
     if not todo:
         return
-    dev = todo[0][1].device
+    dev = todo[0].device
     cur = torch.cuda.current_stream()
     side = _sn_streams.get(dev)
     if side is None:
         side = _sn_streams[dev] = torch.cuda.Stream(device=dev)
     side.wait_stream(cur)          # the optimiser step (and every earlier consumer of the old packs) comes first
     with torch.cuda.stream(side):
-        for _, p in todo:
+        for p in todo:
             tc.prefetch_packs(p)
-        ev = torch.cuda.Event()
-        ev.record(side)
-    for conv, _ in todo:
-        conv.__dict__["_eadgan_pack_ev"] = ev
 
 
 def set_trainable(module, flag):
@@ -219,9 +215,6 @@ def try_run(seq, x):
         return None  # eval-mode BN: per-op path
     params, srcs = [], []
     for st in stages:
-        pack_ev = st.conv.__dict__.pop("_eadgan_pack_ev", None)
-        if pack_ev is not None:        # operands re-packed ahead of time on the side stream (prefetch_packs)
-            torch.cuda.current_stream().wait_event(pack_ev)
         queue = st.conv.__dict__.get("_eadgan_sn_queue")
         if queue:
             # this forward's power iteration was issued ahead of time (prefetch_spectral_norm): adopt its results

@@ -124,12 +124,35 @@ def pack_w_cached(param, direction="fprop", c_alloc=None):
     _note_use(param, "wide", direction, c_alloc)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0]() is param and hit[1] == token:
-        return hit[2]
+        return _adopt(hit)
     out = pack_w(param.detach(), None, direction, c_alloc)
     if hit is None or hit[0]() is not param:
         weakref.finalize(param, _pack_cache.pop, key, None)
-    _pack_cache[key] = (weakref.ref(param), token, out)
+    _pack_cache[key] = (weakref.ref(param), token, out) + _built_on()
     return out
+
+
+_ahead = False      # True while prefetch_packs builds on a side stream: those entries carry an event
+
+
+def _built_on():
+    """(stream the pack was built on, event recorded behind the build or None)"""
+    cur = torch.cuda.current_stream()
+    ev = None
+    if _ahead:
+        ev = torch.cuda.Event()
+        ev.record(cur)
+    return (cur.cuda_stream, ev)
+
+
+def _adopt(hit):
+    """a cached pack that was built ahead of time on ANOTHER stream: the consumer's stream waits for that build"""
+    if hit[4] is not None:
+        cur = torch.cuda.current_stream()
+        if cur.cuda_stream != hit[3]:
+            cur.wait_event(hit[4])
+            hit[2].record_stream(cur)     # allocated on the builder's stream, read on this one
+    return hit[2]
 
 
 def _note_use(param, kind, direction, c_alloc):
@@ -143,12 +166,19 @@ def _note_use(param, kind, direction, c_alloc):
 
 def prefetch_packs(param):
     """Rebuild, on the CURRENT stream, every operand layout ``param`` was consumed in so far (no-op for layouts whose
-    cached pack is still current).  chain.prefetch_packs calls this on a side stream right after an optimiser step."""
-    for kind, direction, c_alloc in tuple(getattr(param, "_eadgan_pack_uses", ())):
-        if kind == "thin":
-            thin_pack_w_cached(param, direction)
-        else:
-            pack_w_cached(param, direction, c_alloc)
+    cached pack is still current).  chain.prefetch_packs calls this on a side stream right after an optimiser step;
+    every entry built here carries an event, and whichever stream later takes it from the cache waits on that event
+    (``_adopt``), so no consumer -- chain executor, per-op module path, autograd worker -- can read a pack early."""
+    global _ahead
+    _ahead = True
+    try:
+        for kind, direction, c_alloc in tuple(getattr(param, "_eadgan_pack_uses", ())):
+            if kind == "thin":
+                thin_pack_w_cached(param, direction)
+            else:
+                pack_w_cached(param, direction, c_alloc)
+    finally:
+        _ahead = False
 
 
 def invalidate_caches():
@@ -277,11 +307,11 @@ def thin_pack_w_cached(param, direction):
     _note_use(param, "thin", direction, None)
     hit = _pack_cache.get(key)
     if hit is not None and hit[0]() is param and hit[1] == token:
-        return hit[2]
+        return _adopt(hit)
     out = thin_pack_w(param.detach(), direction)
     if hit is None or hit[0]() is not param:
         weakref.finalize(param, _pack_cache.pop, key, None)
-    _pack_cache[key] = (weakref.ref(param), token, out)
+    _pack_cache[key] = (weakref.ref(param), token, out) + _built_on()
     return out
 
 
