@@ -1,3 +1,5 @@
+# NOTE: compute-sanitizer is closed on the GPU pool used this round (gpurun answers "compute-sanitizer is closed on this pool");
+# kept for pools where it is available.  The write-bounds check that replaces it is tests/test_guard_gpu.py.
 # compute-sanitizer memcheck over the smoke step and the small-geometry kernel parity tests (bounded: the tool slows
 # kernels by 10-100x).  Writes gpurun_out/r02z_memcheck_*.log; "ERROR SUMMARY: 0 errors" is the pass line.
 export EADGAN_TC_UNITS=8     # small persistent grids: same code paths, far fewer instrumented threads
