@@ -9,8 +9,10 @@
 // Reference call sites: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear of
 // celebA/EAD-GAN_celebA.py:75-122, dSprites/rp.py:66-183, MNIST/EAD-GAN_rpqmnxy.py:77-163.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace {
+namespace cg = cooperative_groups;
 
 constexpr int BM = 64, BN = 64, BK = 16, NT = 256;
 
@@ -28,6 +30,7 @@ struct ConvArgs {
   float slope;
   int M, N, K;       // GEMM extents of this direction
   int m_per_split;   // wgrad only
+  int ksplit;        // fprop / dgrad: CTAs of one thread-block cluster sharing an output tile along K (1 = none)
 };
 
 // ---- fprop / dgrad: C[M,N] = A_gather[M,K] * B[K,N] --------------------------------------
@@ -35,6 +38,7 @@ template <bool DGRAD>
 __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
+  __shared__ float red[BM * BN];   // split-K only: this CTA's partial tile, read by the cluster's first CTA
   const eadgan_conv_desc& d = P.d;
   const int t = threadIdx.x;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -68,7 +72,15 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
   // executes: an 8-CTA launch with K = 1024 took 102 us for 67 MFLOP (ncu r02wd).  Same values, same order.
   const bool lin = rs == 1 && d.h == 1 && d.w == 1 && d.p == 1 && d.q == 1 && d.pad == 0;
 
-  for (int k0 = 0; k0 < P.K; k0 += BK) {
+  // Split K: a launch with few output tiles and a long reduction (a Linear head: 8 tiles, K = 1024) runs as clusters
+  // of `ksplit` CTAs along z; CTA z reduces k tiles [z * per, (z + 1) * per), the partial tiles are summed through
+  // distributed shared memory by the cluster's first CTA in rank order (deterministic) and only that CTA stores.
+  const int k_tiles = (P.K + BK - 1) / BK;
+  const int per = (k_tiles + P.ksplit - 1) / P.ksplit;
+  const int k_begin = (P.ksplit > 1 ? (int)blockIdx.z * per : 0) * BK;
+  const int k_end = P.ksplit > 1 ? min(P.K, ((int)blockIdx.z + 1) * per * BK) : P.K;
+
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
     // ---- gather A
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -149,6 +161,27 @@ __global__ void __launch_bounds__(NT) conv_gemm_kernel(const ConvArgs P) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j] += part[i][j];
     __syncthreads();
+  }
+
+  if (P.ksplit > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[(tx * 4 + i) * BN + ty * 4 + j] = acc[i][j];
+    cluster.sync();
+    if (rank == 0) {
+      for (int r = 1; r < P.ksplit; ++r) {
+        const float* rr = cluster.map_shared_rank(red, r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] += rr[(tx * 4 + i) * BN + ty * 4 + j];
+      }
+    }
+    cluster.sync();        // nobody leaves while its partial tile may still be read
+    if (rank != 0) return;
   }
 
   // ---- epilogue: + bias, activation, strided store
@@ -328,6 +361,32 @@ __global__ void copy4_kernel(eadgan_tensor4 src, eadgan_tensor4 dst, int n, int 
   }
 }
 
+// few output tiles and a long reduction: clusters of 2 / 4 / 8 CTAs along K (see conv_gemm_kernel)
+int pick_ksplit(dim3 grid, int K) {
+  const int ctas = (int)(grid.x * grid.y), k_tiles = (K + BK - 1) / BK;
+  if (ctas > 37 || k_tiles < 16) return 1;
+  int ks = 8;
+  while (ks > 1 && (k_tiles / ks < 4 || ctas * ks > 296)) ks >>= 1;
+  return ks;
+}
+
+template <bool DGRAD>
+int launch_conv_gemm(ConvArgs& P, dim3 grid, cudaStream_t st) {
+  P.ksplit = pick_ksplit(grid, P.K);
+  if (P.ksplit == 1) {
+    conv_gemm_kernel<DGRAD><<<grid, NT, 0, st>>>(P);
+    return 0;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid.x, grid.y, P.ksplit); cfg.blockDim = dim3(NT); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = P.ksplit;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  EG_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<DGRAD>, P));
+  return 0;
+}
+
 int check_desc(const eadgan_conv_desc* d) {
   EG_REQUIRE(d != nullptr, EADGAN_ERR_INVALID, "conv desc is NULL");
   EG_REQUIRE(d->n > 0 && d->c > 0 && d->h > 0 && d->w > 0 && d->k > 0 && d->r > 0 && d->s > 0 &&
@@ -351,7 +410,7 @@ extern "C" int eadgan_conv_fprop(const eadgan_conv_desc* d, const eadgan_tensor4
   if (mask && mask_act != EADGAN_ACT_NONE) { P.mask = *mask; P.mask_act = mask_act; P.mask_slope = mask_slope; }
   P.M = d->n * d->p * d->q; P.N = d->k; P.K = d->c * d->r * d->s;
   dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN);
-  conv_gemm_kernel<false><<<grid, NT, 0, (cudaStream_t)stream>>>(P);
+  if (int e = launch_conv_gemm<false>(P, grid, (cudaStream_t)stream)) return e;
   EG_LAUNCH_CHECK("conv_gemm_kernel<fprop>");
   return 0;
 }
@@ -366,7 +425,7 @@ extern "C" int eadgan_conv_dgrad(const eadgan_conv_desc* d, const eadgan_tensor4
   if (mask && mask_act != EADGAN_ACT_NONE) { P.mask = *mask; P.mask_act = mask_act; P.mask_slope = mask_slope; }
   P.M = d->n * d->h * d->w; P.N = d->c; P.K = d->k * d->r * d->s;
   dim3 grid((P.M + BM - 1) / BM, (P.N + BN - 1) / BN);
-  conv_gemm_kernel<true><<<grid, NT, 0, (cudaStream_t)stream>>>(P);
+  if (int e = launch_conv_gemm<true>(P, grid, (cudaStream_t)stream)) return e;
   EG_LAUNCH_CHECK("conv_gemm_kernel<dgrad>");
   return 0;
 }
